@@ -1,0 +1,472 @@
+// C ABI of atlasqtl_b200 (include/atlasqtl_b200.h): context management, host <-> device layout
+// conversion and kernel launches.  No torch, no CPU fallback: every entry point either runs the CUDA
+// path or returns an error code.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/atlasqtl_b200.h"
+#include "aq_stream.cuh"
+#include "aq_sweep.cuh"
+
+using namespace aq;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define AQ_CUDA(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (expr);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            cudaGetLastError();                                                                         \
+            return fail(e_ == cudaErrorMemoryAllocation ? AQ_ENOMEM : AQ_ECUDA,                         \
+                        std::string(#expr) + ": " + cudaGetErrorString(e_));                            \
+        }                                                                                               \
+    } while (0)
+
+// ---- kernel configurations (SweepCfg<WS, WT, MT, NT>): picked by n at aq_create time
+using CfgA16 = SweepCfg<8, 1, 2, 16>;  // n <= 1024, 16 traits / tile
+using CfgA8 = SweepCfg<8, 1, 2, 8>;    // n <= 512 ... only used when it wastes less padding
+using CfgB16 = SweepCfg<4, 2, 2, 16>;  // n <= 512, 32 traits / tile
+using CfgB8 = SweepCfg<4, 2, 2, 8>;    // n <= 256
+using CfgC16 = SweepCfg<2, 4, 2, 16>;  // n <= 256, 64 traits / tile
+using CfgC8 = SweepCfg<2, 4, 2, 8>;    // n <= 128
+
+struct CfgInfo {
+    int id, n_pad, xs, kT, threads;
+    size_t smem, tile_doubles;
+};
+template <class C>
+CfgInfo info(int id) {
+    return CfgInfo{id, C::kNPad, C::kXS, C::kT, C::kThreads, C::kSmemBytes, C::kTileDoubles};
+}
+
+bool pick_cfg(int n, CfgInfo* out) {
+    if (n <= 128) *out = info<CfgC8>(5);
+    else if (n <= 256) *out = info<CfgC16>(4);
+    else if (n <= 512) *out = info<CfgB16>(2);
+    else if (n <= 1024) *out = info<CfgA16>(0);
+    else return false;
+    return true;
+}
+
+}  // namespace
+
+struct aq_ctx {
+    int device = 0, n = 0, p = 0, q = 0;
+    int p_pad = 0, q_pad = 0, nb = 0, ntiles = 0, sm_count = 0;
+    CfgInfo cfg{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double *xraw = nullptr, *xtiles = nullptr, *ymat = nullptr, *resid = nullptr;
+    double *gam = nullptr, *mu = nullptr, *dtab = nullptr, *wtab = nullptr, *i0tab = nullptr;
+    double *tvec = nullptr;     // 3 x q_pad: tau, log_tau, sig2_beta
+    double *ovec = nullptr;     // 5 x q_pad: cs_gam, cs_gmu2, cs_b2, rsq, cs_z
+    double *theta = nullptr, *zeta = nullptr, *rowsum = nullptr, *partials = nullptr, *scalar = nullptr;
+    double *stage = nullptr;    // transposition staging: stage_cols x p doubles
+    int stage_cols = 0;
+    size_t n_partials = 0;
+    int* order_dev = nullptr;
+    std::vector<int32_t> order;
+    std::vector<double> hbuf;   // pinned-size-agnostic host scratch
+    bool have_state = false, have_tables = false;
+    int64_t launches = 0;
+    float last_ms = 0.f;
+};
+
+namespace {
+
+template <class C>
+int launch_sweep_t(aq_ctx* c, const SweepParams& P) {
+    static bool attr_done[64] = {false};
+    if (!attr_done[c->device]) {
+        AQ_CUDA(cudaFuncSetAttribute(sweep_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
+        attr_done[c->device] = true;
+    }
+    const int grid = std::min(c->ntiles, c->sm_count);
+    AQ_CUDA(cudaEventRecord(c->ev0, c->stream));
+    sweep_kernel<C><<<grid, C::kThreads, C::kSmemBytes, c->stream>>>(P);
+    AQ_CUDA(cudaGetLastError());
+    AQ_CUDA(cudaEventRecord(c->ev1, c->stream));
+    c->launches++;
+    return AQ_OK;
+}
+
+int launch_sweep(aq_ctx* c, int mode, double cc, double log_sig2_inv) {
+    SweepParams P;
+    P.xtiles = c->xtiles;
+    P.tile_stride = c->cfg.tile_doubles;
+    P.nb = c->nb;
+    P.ntiles = c->ntiles;
+    P.q = c->q;
+    P.q_pad = c->q_pad;
+    P.ld_resid = c->cfg.n_pad;
+    P.resid = c->resid;
+    P.gam = c->gam;
+    P.mu = c->mu;
+    P.dtab = c->dtab;
+    P.wtab = c->wtab;
+    P.i0tab = c->i0tab;
+    P.tau = c->tvec;
+    P.log_tau = c->tvec + c->q_pad;
+    P.sig2_beta = c->tvec + 2 * (size_t)c->q_pad;
+    P.c = cc;
+    P.log_sig2_inv = log_sig2_inv;
+    P.cs_gam = c->ovec;
+    P.cs_gmu2 = c->ovec + c->q_pad;
+    P.cs_b2 = c->ovec + 2 * (size_t)c->q_pad;
+    P.rsq = c->ovec + 3 * (size_t)c->q_pad;
+    P.cs_z = c->ovec + 4 * (size_t)c->q_pad;
+    P.mode = mode;
+    switch (c->cfg.id) {
+        case 0: return launch_sweep_t<CfgA16>(c, P);
+        case 2: return launch_sweep_t<CfgB16>(c, P);
+        case 4: return launch_sweep_t<CfgC16>(c, P);
+        case 5: return launch_sweep_t<CfgC8>(c, P);
+    }
+    return fail(AQ_EUNSUPPORTED, "no kernel configuration");
+}
+
+int upload_pxq(aq_ctx* c, const double* host, double* dev) {
+    // host: p x q column-major.  Staged in chunks of stage_cols traits, transposed on the device.
+    for (int k0 = 0; k0 < c->q; k0 += c->stage_cols) {
+        const int kc = std::min(c->stage_cols, c->q - k0);
+        AQ_CUDA(cudaMemcpyAsync(c->stage, host + (size_t)k0 * c->p, sizeof(double) * (size_t)kc * c->p,
+                                cudaMemcpyHostToDevice, c->stream));
+        dim3 grid((c->p + 31) / 32, (kc + 31) / 32), block(32, 8);
+        cm_to_dev_kernel<<<grid, block, 0, c->stream>>>(c->stage, c->p, kc, k0, c->q_pad, dev);
+        AQ_CUDA(cudaGetLastError());
+        c->launches++;
+    }
+    return AQ_OK;
+}
+
+int download_pxq(aq_ctx* c, const double* a, const double* b, int op, double* host) {
+    for (int k0 = 0; k0 < c->q; k0 += c->stage_cols) {
+        const int kc = std::min(c->stage_cols, c->q - k0);
+        dim3 grid((c->p + 31) / 32, (kc + 31) / 32), block(32, 8);
+        dev_to_cm_kernel<<<grid, block, 0, c->stream>>>(a, b, op, c->p, kc, k0, c->q_pad, c->stage);
+        AQ_CUDA(cudaGetLastError());
+        c->launches++;
+        AQ_CUDA(cudaMemcpyAsync(host + (size_t)k0 * c->p, c->stage, sizeof(double) * (size_t)kc * c->p,
+                                cudaMemcpyDeviceToHost, c->stream));
+        AQ_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return AQ_OK;
+}
+
+int fetch_outputs(aq_ctx* c, double* o0, double* o1, double* o2, double* o3, double* o4) {
+    double* outs[5] = {o0, o1, o2, o3, o4};
+    bool any = false;
+    for (double* o : outs) any = any || (o != nullptr);
+    if (!any) return AQ_OK;
+    c->hbuf.resize(5 * (size_t)c->q_pad);
+    AQ_CUDA(cudaMemcpyAsync(c->hbuf.data(), c->ovec, sizeof(double) * 5 * (size_t)c->q_pad, cudaMemcpyDeviceToHost,
+                            c->stream));
+    AQ_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 5; ++i)
+        if (outs[i]) std::memcpy(outs[i], c->hbuf.data() + (size_t)i * c->q_pad, sizeof(double) * c->q);
+    return AQ_OK;
+}
+
+int retile(aq_ctx* c) {
+    AQ_CUDA(cudaMemcpyAsync(c->order_dev, c->order.data(), sizeof(int32_t) * c->p, cudaMemcpyHostToDevice, c->stream));
+    build_tiles_kernel<<<c->nb, 256, 0, c->stream>>>(c->xraw, c->order_dev, c->n, c->p, c->cfg.xs, c->cfg.tile_doubles,
+                                                     c->xtiles);
+    AQ_CUDA(cudaGetLastError());
+    gram_band_kernel<<<c->nb, 128, 0, c->stream>>>(c->xtiles, c->cfg.n_pad, c->cfg.xs, c->cfg.tile_doubles);
+    AQ_CUDA(cudaGetLastError());
+    c->launches += 2;
+    return AQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* aq_last_error(void) { return g_err.c_str(); }
+int aq_version(void) { return 100; }
+
+int aq_device_info(int device, int* sm_count, int64_t* free_bytes, int64_t* total_bytes) {
+    int ndev = 0;
+    AQ_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(AQ_EINVAL, "device index out of range");
+    AQ_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    AQ_CUDA(cudaGetDeviceProperties(&prop, device));
+    size_t fr = 0, tot = 0;
+    AQ_CUDA(cudaMemGetInfo(&fr, &tot));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (free_bytes) *free_bytes = (int64_t)fr;
+    if (total_bytes) *total_bytes = (int64_t)tot;
+    return AQ_OK;
+}
+
+int aq_destroy(aq_ctx* c) {
+    if (!c) return AQ_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    double* bufs[] = {c->xraw, c->xtiles, c->ymat, c->resid, c->gam, c->mu, c->dtab, c->wtab, c->i0tab, c->tvec,
+                      c->ovec, c->theta, c->zeta, c->rowsum, c->partials, c->scalar, c->stage};
+    for (double* b : bufs)
+        if (b) cudaFree(b);
+    if (c->order_dev) cudaFree(c->order_dev);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return AQ_OK;
+}
+
+int aq_create(aq_ctx** out, int device, int n, int p, int q_local, const double* X, const double* Y) {
+    if (!out || !X || !Y) return fail(AQ_EINVAL, "aq_create: NULL argument");
+    if (n < 2 || p < 1 || q_local < 1) return fail(AQ_EINVAL, "aq_create: need n >= 2, p >= 1, q >= 1");
+    CfgInfo cfg;
+    if (!pick_cfg(n, &cfg))
+        return fail(AQ_EUNSUPPORTED, "aq_create: n > 1024 needs the sample-split (cluster) kernel, not in this build");
+    int sm = 0;
+    int rc = aq_device_info(device, &sm, nullptr, nullptr);
+    if (rc != AQ_OK) return rc;
+    aq_ctx* c = new aq_ctx();
+    c->device = device;
+    c->n = n;
+    c->p = p;
+    c->q = q_local;
+    c->cfg = cfg;
+    c->sm_count = sm;
+    c->p_pad = (p + kBlk - 1) / kBlk * kBlk;
+    c->q_pad = (q_local + cfg.kT - 1) / cfg.kT * cfg.kT;
+    c->nb = c->p_pad / kBlk;
+    c->ntiles = c->q_pad / cfg.kT;
+    const size_t pq = (size_t)c->p_pad * c->q_pad;
+    c->stage_cols = (int)std::max<size_t>(1, std::min<size_t>((size_t)q_local, ((size_t)256 << 20) / (sizeof(double) * (size_t)p)));
+    c->n_partials = (size_t)((c->q + 255) / 256) * ((c->p + kTabRowsPerBlock - 1) / kTabRowsPerBlock);
+#define AQ_ALLOC(ptr, count)                                                              \
+    do {                                                                                  \
+        cudaError_t e_ = cudaMalloc((void**)&(ptr), sizeof(*(ptr)) * (size_t)(count));    \
+        if (e_ != cudaSuccess) {                                                          \
+            cudaGetLastError();                                                           \
+            aq_destroy(c);                                                                \
+            return fail(AQ_ENOMEM, std::string("cudaMalloc ") + #ptr + ": " + cudaGetErrorString(e_)); \
+        }                                                                                 \
+    } while (0)
+    AQ_ALLOC(c->xraw, (size_t)n * p);
+    AQ_ALLOC(c->xtiles, (size_t)c->nb * cfg.tile_doubles);
+    AQ_ALLOC(c->ymat, (size_t)c->q_pad * cfg.n_pad);
+    AQ_ALLOC(c->resid, (size_t)c->q_pad * cfg.n_pad);
+    AQ_ALLOC(c->gam, pq);
+    AQ_ALLOC(c->mu, pq);
+    AQ_ALLOC(c->dtab, pq);
+    AQ_ALLOC(c->wtab, pq);
+    AQ_ALLOC(c->i0tab, pq);
+    AQ_ALLOC(c->tvec, 3 * (size_t)c->q_pad);
+    AQ_ALLOC(c->ovec, 5 * (size_t)c->q_pad);
+    AQ_ALLOC(c->theta, c->p_pad);
+    AQ_ALLOC(c->zeta, c->q_pad);
+    AQ_ALLOC(c->rowsum, c->p_pad);
+    AQ_ALLOC(c->partials, c->n_partials);
+    AQ_ALLOC(c->scalar, 8);
+    AQ_ALLOC(c->stage, (size_t)c->stage_cols * p);
+    AQ_ALLOC(c->order_dev, c->p_pad);
+#undef AQ_ALLOC
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->ymat, 0, sizeof(double) * (size_t)c->q_pad * cfg.n_pad, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->gam, 0, sizeof(double) * pq, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->mu, 0, sizeof(double) * pq, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->dtab, 0, sizeof(double) * pq, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->wtab, 0, sizeof(double) * pq, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->i0tab, 0, sizeof(double) * pq, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->ovec, 0, sizeof(double) * 5 * (size_t)c->q_pad, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->rowsum, 0, sizeof(double) * c->p_pad, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->xraw, X, sizeof(double) * (size_t)n * p, cudaMemcpyHostToDevice, c->stream);
+    // Y: n x q column-major -> [q_pad][n_pad] rows (same orientation, padded leading dimension)
+    if (e == cudaSuccess)
+        e = cudaMemcpy2DAsync(c->ymat, sizeof(double) * cfg.n_pad, Y, sizeof(double) * n, sizeof(double) * n, q_local,
+                              cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        aq_destroy(c);
+        return fail(AQ_ECUDA, std::string("aq_create: ") + cudaGetErrorString(e));
+    }
+    // benign per-trait constants for padding traits
+    fill_kernel<<<64, 256, 0, c->stream>>>(c->tvec, 3 * (size_t)c->q_pad, 1.0);
+    c->launches++;
+    c->order.resize(p);
+    for (int j = 0; j < p; ++j) c->order[j] = j;
+    rc = retile(c);
+    if (rc == AQ_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(AQ_ECUDA, "aq_create: sync failed");
+    if (rc != AQ_OK) {
+        aq_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return AQ_OK;
+}
+
+int aq_dims(const aq_ctx* c, int* n, int* p, int* q_local, int* p_pad, int* q_pad) {
+    if (!c) return fail(AQ_EINVAL, "NULL context");
+    if (n) *n = c->n;
+    if (p) *p = c->p;
+    if (q_local) *q_local = c->q;
+    if (p_pad) *p_pad = c->p_pad;
+    if (q_pad) *q_pad = c->q_pad;
+    return AQ_OK;
+}
+
+int aq_set_order(aq_ctx* c, const int32_t* shuffled_ind) {
+    if (!c) return fail(AQ_EINVAL, "NULL context");
+    AQ_CUDA(cudaSetDevice(c->device));
+    std::vector<int32_t> ord(c->p);
+    if (shuffled_ind) {
+        std::vector<char> seen(c->p, 0);
+        for (int b = 0; b < c->p; ++b) {
+            const int32_t j = shuffled_ind[b];
+            if (j < 0 || j >= c->p || seen[j]) return fail(AQ_EINVAL, "aq_set_order: shuffled_ind is not a permutation of 0..p-1");
+            seen[j] = 1;
+            ord[b] = j;
+        }
+    } else {
+        for (int j = 0; j < c->p; ++j) ord[j] = j;
+    }
+    if (ord == c->order) return AQ_OK;
+    c->order.swap(ord);
+    int rc = retile(c);
+    if (rc != AQ_OK) return rc;
+    AQ_CUDA(cudaStreamSynchronize(c->stream));
+    return AQ_OK;
+}
+
+int aq_set_state(aq_ctx* c, const double* gam_vb, const double* mu_beta_vb, double* colsum_gam, double* colsum_gam_mu2,
+                 double* colsum_beta2, double* resid_sq) {
+    if (!c || !gam_vb || !mu_beta_vb) return fail(AQ_EINVAL, "aq_set_state: NULL argument");
+    AQ_CUDA(cudaSetDevice(c->device));
+    int rc = upload_pxq(c, gam_vb, c->gam);
+    if (rc != AQ_OK) return rc;
+    rc = upload_pxq(c, mu_beta_vb, c->mu);
+    if (rc != AQ_OK) return rc;
+    AQ_CUDA(cudaMemcpyAsync(c->resid, c->ymat, sizeof(double) * (size_t)c->q_pad * c->cfg.n_pad, cudaMemcpyDeviceToDevice,
+                            c->stream));
+    rc = launch_sweep(c, /*mode=*/1, 1.0, 0.0);
+    if (rc != AQ_OK) return rc;
+    c->have_state = true;
+    rc = fetch_outputs(c, colsum_gam, colsum_gam_mu2, colsum_beta2, resid_sq, nullptr);
+    if (rc != AQ_OK) return rc;
+    AQ_CUDA(cudaStreamSynchronize(c->stream));
+    return AQ_OK;
+}
+
+int aq_get_state(aq_ctx* c, double* gam_vb, double* mu_beta_vb, double* beta_vb) {
+    if (!c) return fail(AQ_EINVAL, "NULL context");
+    if (!c->have_state) return fail(AQ_ESTATE, "aq_get_state before aq_set_state");
+    AQ_CUDA(cudaSetDevice(c->device));
+    int rc = AQ_OK;
+    if (gam_vb && (rc = download_pxq(c, c->gam, nullptr, 0, gam_vb)) != AQ_OK) return rc;
+    if (mu_beta_vb && (rc = download_pxq(c, c->mu, nullptr, 0, mu_beta_vb)) != AQ_OK) return rc;
+    if (beta_vb && (rc = download_pxq(c, c->gam, c->mu, 1, beta_vb)) != AQ_OK) return rc;
+    return AQ_OK;
+}
+
+int aq_get_residual(aq_ctx* c, double* resid) {
+    if (!c || !resid) return fail(AQ_EINVAL, "NULL argument");
+    if (!c->have_state) return fail(AQ_ESTATE, "aq_get_residual before aq_set_state");
+    AQ_CUDA(cudaSetDevice(c->device));
+    AQ_CUDA(cudaMemcpy2DAsync(resid, sizeof(double) * c->n, c->resid, sizeof(double) * c->cfg.n_pad, sizeof(double) * c->n,
+                              c->q, cudaMemcpyDeviceToHost, c->stream));
+    AQ_CUDA(cudaStreamSynchronize(c->stream));
+    return AQ_OK;
+}
+
+int aq_refresh_tables(aq_ctx* c, const double* theta_vb, const double* zeta_vb, double c_next, double* elbo_b_part) {
+    if (!c || !theta_vb || !zeta_vb) return fail(AQ_EINVAL, "aq_refresh_tables: NULL argument");
+    if (!(c_next > 0.0)) return fail(AQ_EINVAL, "aq_refresh_tables: c_next must be positive");
+    if (elbo_b_part && !c->have_state) return fail(AQ_ESTATE, "aq_refresh_tables: ELBO part needs a state");
+    AQ_CUDA(cudaSetDevice(c->device));
+    AQ_CUDA(cudaMemcpyAsync(c->theta, theta_vb, sizeof(double) * c->p, cudaMemcpyHostToDevice, c->stream));
+    AQ_CUDA(cudaMemcpyAsync(c->zeta, zeta_vb, sizeof(double) * c->q, cudaMemcpyHostToDevice, c->stream));
+    const int c_is_one = std::fabs(c_next - 1.0) < 1.5e-8;  // isTRUE(all.equal(c, 1)), R/update_vb.R:219
+    dim3 grid((c->q + 255) / 256, (c->p + kTabRowsPerBlock - 1) / kTabRowsPerBlock);
+    tables_kernel<<<grid, 256, 0, c->stream>>>(c->theta, c->zeta, c->p, c->q, c->q_pad, c_is_one ? 1.0 : std::sqrt(c_next),
+                                               c_is_one, c->gam, c->dtab, c->wtab, c->i0tab, elbo_b_part ? 1 : 0,
+                                               c->partials);
+    AQ_CUDA(cudaGetLastError());
+    c->launches++;
+    if (elbo_b_part) {
+        sum_partials_kernel<<<1, 1024, 0, c->stream>>>(c->partials, c->n_partials, c->scalar);
+        AQ_CUDA(cudaGetLastError());
+        c->launches++;
+        AQ_CUDA(cudaMemcpyAsync(elbo_b_part, c->scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    AQ_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_tables = true;
+    return AQ_OK;
+}
+
+int aq_sweep(aq_ctx* c, double cc, double log_sig2_inv_vb, const double* tau_vb, const double* log_tau_vb,
+             const double* sig2_beta_vb, double* colsum_gam, double* colsum_gam_mu2, double* colsum_beta2,
+             double* resid_sq, double* colsum_zpart) {
+    if (!c || !tau_vb || !log_tau_vb || !sig2_beta_vb) return fail(AQ_EINVAL, "aq_sweep: NULL argument");
+    if (!c->have_state) return fail(AQ_ESTATE, "aq_sweep before aq_set_state");
+    if (!c->have_tables) return fail(AQ_ESTATE, "aq_sweep before aq_refresh_tables");
+    if (!(cc > 0.0)) return fail(AQ_EINVAL, "aq_sweep: c must be positive");
+    AQ_CUDA(cudaSetDevice(c->device));
+    AQ_CUDA(cudaMemcpyAsync(c->tvec, tau_vb, sizeof(double) * c->q, cudaMemcpyHostToDevice, c->stream));
+    AQ_CUDA(cudaMemcpyAsync(c->tvec + c->q_pad, log_tau_vb, sizeof(double) * c->q, cudaMemcpyHostToDevice, c->stream));
+    AQ_CUDA(cudaMemcpyAsync(c->tvec + 2 * (size_t)c->q_pad, sig2_beta_vb, sizeof(double) * c->q, cudaMemcpyHostToDevice,
+                            c->stream));
+    int rc = launch_sweep(c, /*mode=*/0, cc, log_sig2_inv_vb);
+    if (rc != AQ_OK) return rc;
+    rc = fetch_outputs(c, colsum_gam, colsum_gam_mu2, colsum_beta2, resid_sq, colsum_zpart);
+    if (rc != AQ_OK) return rc;
+    AQ_CUDA(cudaStreamSynchronize(c->stream));
+    AQ_CUDA(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+    return AQ_OK;
+}
+
+int aq_rowsums_zpart_dev(aq_ctx* c, double** rowsum_zpart_dev) {
+    if (!c || !rowsum_zpart_dev) return fail(AQ_EINVAL, "NULL argument");
+    if (!c->have_state || !c->have_tables) return fail(AQ_ESTATE, "aq_rowsums_zpart before state/tables");
+    AQ_CUDA(cudaSetDevice(c->device));
+    rowsums_kernel<<<(c->p + 7) / 8, 256, 0, c->stream>>>(c->gam, c->wtab, c->i0tab, c->p, c->q, c->q_pad, c->rowsum);
+    AQ_CUDA(cudaGetLastError());
+    c->launches++;
+    AQ_CUDA(cudaStreamSynchronize(c->stream));
+    *rowsum_zpart_dev = c->rowsum;
+    return AQ_OK;
+}
+
+int aq_rowsums_zpart(aq_ctx* c, double* rowsum_zpart) {
+    if (!rowsum_zpart) return fail(AQ_EINVAL, "NULL argument");
+    double* dev = nullptr;
+    int rc = aq_rowsums_zpart_dev(c, &dev);
+    if (rc != AQ_OK) return rc;
+    AQ_CUDA(cudaMemcpy(rowsum_zpart, dev, sizeof(double) * c->p, cudaMemcpyDeviceToHost));
+    return AQ_OK;
+}
+
+int64_t aq_launch_count(const aq_ctx* c) { return c ? c->launches : 0; }
+
+int aq_last_sweep_ms(const aq_ctx* c, float* ms) {
+    if (!c || !ms) return fail(AQ_EINVAL, "NULL argument");
+    *ms = c->last_ms;
+    return AQ_OK;
+}
+
+int aq_sync(aq_ctx* c) {
+    if (!c) return fail(AQ_EINVAL, "NULL context");
+    AQ_CUDA(cudaSetDevice(c->device));
+    AQ_CUDA(cudaStreamSynchronize(c->stream));
+    return AQ_OK;
+}
+
+}  // extern "C"

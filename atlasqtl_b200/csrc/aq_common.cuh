@@ -1,0 +1,91 @@
+// Shared device helpers for the atlasqtl_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace aq {
+
+// ---------------------------------------------------------------- geometry shared by host and device
+constexpr int kBlk = 8;          // SNPs per block: one m8n8k4 N-tile (S GEMM) / two K-steps (update GEMM)
+constexpr int kTileTail = 144;   // doubles appended to each X tile: 128 (Gram band) + 16 (8 x int32 SNP ids, padded)
+
+// X tile image in global memory (one per block of kBlk SNPs in sweep order), copied verbatim into
+// shared memory by one bulk copy:
+//   [kBlk][xs]  doubles   X columns of the block's SNPs, samples contiguous, sample index XOR-swizzled
+//                         (i ^ ((t & 2) << 1)) so that both MMA operand patterns are bank-conflict free
+//   [kBlk][16]  doubles   Gram band: g[t][0..7] = X_t' X_u, u in the PREVIOUS block; g[t][8+u] = X_t' X_u, u in this block
+//   [kBlk]      int32     SNP index (row of the p x q arrays) of slot t, -1 for padding slots; then 8 int32 of padding
+__host__ __device__ inline size_t tile_doubles(int xs) { return (size_t)kBlk * xs + kTileTail; }
+__host__ __device__ inline int swz(int i, int t) { return i ^ ((t & 2) << 1); }
+
+// ---------------------------------------------------------------- mbarrier / bulk-copy PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 1-D bulk copy global -> shared through the TMA engine; completion is signalled on `bar` (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------- fp64 tensor-core MMA (SASS: DMMA.8x8x4)
+// D(8x8) += A(8x4) * B(4x8).  Lane (g = lane>>2, l = lane&3) holds A[g][l], B[l][g], D[g][2l], D[g][2l+1].
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------- normal-distribution helpers
+// log Phi(x), accurate in both tails: Phi(x) = erfc(-x/sqrt2)/2; for x < -1 go through the scaled
+// complementary error function so that nothing underflows; for x > 0 use log1p(-Q(x)).
+// (Replaces R's pnorm(x, log.p = TRUE), R/atlasqtl_global_local_core.R:62-63,294-295.)
+__device__ __forceinline__ double log_ndtr(double x) {
+    const double rs2 = 0.70710678118654752440;
+    if (x < -1.0) {
+        double t = -x * rs2;
+        return log(0.5 * erfcx(t)) - t * t;
+    }
+    if (x > 0.0) return log1p(-0.5 * erfc(x * rs2));
+    return log(0.5 * erfc(-x * rs2));
+}
+
+}  // namespace aq

@@ -1,0 +1,184 @@
+// Streaming / set-up kernels around the sweep: X tiling + Gram band, layout transposes, the
+// log-normal-CDF table pass (with ELBO term B), and the row sums of Z.
+#pragma once
+#include "aq_common.cuh"
+
+namespace aq {
+
+// ---------------------------------------------------------------- X tiles (one CTA per SNP block)
+// xraw: [p][n] (column j of the R matrix X contiguous).  order: sweep position -> SNP index.
+__global__ void build_tiles_kernel(const double* __restrict__ xraw, const int* __restrict__ order, int n, int p,
+                                   int xs, size_t tile_stride, double* __restrict__ tiles) {
+    const int b = blockIdx.x;
+    double* tile = tiles + (size_t)b * tile_stride;
+    for (int t = 0; t < kBlk; ++t) {
+        const int pos = b * kBlk + t;
+        const int j = pos < p ? order[pos] : -1;
+        for (int i = threadIdx.x; i < xs; i += blockDim.x) {
+            // physical slot i holds logical sample swz(i, t) (the XOR is an involution)
+            const int li = swz(i, t);
+            tile[t * xs + i] = (j >= 0 && li < n) ? xraw[(size_t)j * n + li] : 0.0;
+        }
+        if (threadIdx.x == 0) reinterpret_cast<int*>(tile + kBlk * xs + 128)[t] = j;
+    }
+    if (threadIdx.x < 8) reinterpret_cast<int*>(tile + kBlk * xs + 128)[8 + threadIdx.x] = 0;
+}
+
+// Gram band of block b: g[t][u] = X_t' X_u for u in block b-1 (u = 0..7) and in block b (u = 8..15).
+// 128 threads, one (t, u) pair each; reads the freshly built tiles.
+__global__ void gram_band_kernel(double* __restrict__ tiles, int n_pad, int xs, size_t tile_stride) {
+    const int b = blockIdx.x;
+    const int t = threadIdx.x >> 4, u = threadIdx.x & 15;
+    double* tile = tiles + (size_t)b * tile_stride;
+    double acc = 0.0;
+    if (u >= 8 || b > 0) {
+        const double* other = (u >= 8) ? tile : tile - tile_stride;
+        const int uu = u & 7;
+        const double* xt = tile + t * xs;
+        const double* xu = other + uu * xs;
+        for (int i = 0; i < n_pad; ++i) acc = fma(xt[swz(i, t)], xu[swz(i, uu)], acc);
+    }
+    tile[kBlk * xs + t * 16 + u] = acc;
+}
+
+// ---------------------------------------------------------------- layout transposes (32 x 32 smem tiles)
+// src: kc columns of an R matrix, column-major with leading dimension p  (src[kk * p + j])
+// dst: device layout [p_pad][q_pad], trait-contiguous                    (dst[j * q_pad + k_first + kk])
+__global__ void cm_to_dev_kernel(const double* __restrict__ src, int p, int kc, int k_first, int q_pad,
+                                 double* __restrict__ dst) {
+    __shared__ double tile[32][33];
+    const int j0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int kk = c0 + r, j = j0 + threadIdx.x;
+        tile[r][threadIdx.x] = (kk < kc && j < p) ? src[(size_t)kk * p + j] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int j = j0 + r, kk = c0 + threadIdx.x;
+        if (j < p && kk < kc) dst[(size_t)j * q_pad + k_first + kk] = tile[threadIdx.x][r];
+    }
+}
+// inverse; op: 0 copy a, 1 product a * b (beta_vb = gam_vb * mu_beta_vb)
+__global__ void dev_to_cm_kernel(const double* __restrict__ a, const double* __restrict__ b2, int op, int p, int kc,
+                                 int k_first, int q_pad, double* __restrict__ dst) {
+    __shared__ double tile[32][33];
+    const int j0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int j = j0 + r, kk = c0 + threadIdx.x;
+        double v = 0.0;
+        if (j < p && kk < kc) {
+            const size_t off = (size_t)j * q_pad + k_first + kk;
+            v = a[off];
+            if (op == 1) v *= b2[off];
+        }
+        tile[r][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int kk = c0 + r, j = j0 + threadIdx.x;
+        if (kk < kc && j < p) dst[(size_t)kk * p + j] = tile[threadIdx.x][r];
+    }
+}
+
+__global__ void fill_kernel(double* __restrict__ x, size_t nelem, double v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nelem; i += (size_t)gridDim.x * blockDim.x) x[i] = v;
+}
+
+// ---------------------------------------------------------------- table pass (K1)
+// For every (j, k): u = theta_j + zeta_k; lp = log Phi(u); lq = log Phi(-u);
+//   D = lq - lp;  at U = sqrt(c) u:  imr1 = phi(U)/Phi(U) (>= -U), imr0 = -phi(U)/(1 - Phi(U)) (<= -U)
+//   W = imr1 - imr0;  I0 = imr0.                             (R/utils.R:172-191, R/update_vb.R:217-234)
+// Optional ELBO-B part (R/elbo.R:19-26): sum gam lp + (1-gam) lq - gam log(gam+eps) - (1-gam) log(1-gam+eps).
+// Grid: blockIdx.y strides over rows j, blockIdx.x * blockDim.x covers traits k (coalesced).
+constexpr int kTabRowsPerBlock = 8;
+__global__ void __launch_bounds__(256) tables_kernel(const double* __restrict__ theta, const double* __restrict__ zeta, int p,
+                                                     int q, int q_pad, double sqrt_c, int c_is_one,
+                                                     const double* __restrict__ gam, double* __restrict__ dtab,
+                                                     double* __restrict__ wtab, double* __restrict__ i0tab, int want_elbo,
+                                                     double* __restrict__ partials) {
+    const double kLogSqrt2Pi = 0.91893853320467274178;
+    const double eps = 1.8189894035458565e-12;  // .Machine$double.eps^0.75 (R/elbo.R:15)
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    double part = 0.0;
+    if (k < q) {
+        const double zk = zeta[k];
+        const int j0 = blockIdx.y * kTabRowsPerBlock;
+#pragma unroll 1
+        for (int r = 0; r < kTabRowsPerBlock; ++r) {
+            const int j = j0 + r;
+            if (j >= p) break;
+            const size_t off = (size_t)j * q_pad + k;
+            const double u = theta[j] + zk;
+            const double lp = log_ndtr(u), lq = log_ndtr(-u);
+            dtab[off] = lq - lp;
+            double U = u, lpU = lp, lqU = lq;
+            if (!c_is_one) {
+                U = sqrt_c * u;
+                lpU = log_ndtr(U);
+                lqU = log_ndtr(-U);
+            }
+            const double e = -0.5 * U * U - kLogSqrt2Pi;
+            double m1 = exp(e - lpU);
+            if (m1 < -U) m1 = -U;
+            double m0 = -exp(e - lqU);
+            if (m0 > -U) m0 = -U;
+            wtab[off] = m1 - m0;
+            i0tab[off] = m0;
+            if (want_elbo) {
+                const double gm = gam[off];
+                part += gm * lp + (1.0 - gm) * lq - gm * log(gm + eps) - (1.0 - gm) * log(1.0 - gm + eps);
+            }
+        }
+    }
+    if (want_elbo) {
+        __shared__ double red[8];
+        part = warp_sum(part);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int w = 0; w < 8; ++w) s += red[w];
+            partials[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
+        }
+    }
+}
+
+// deterministic sum of `n` doubles by one block of 1024 threads
+__global__ void sum_partials_kernel(const double* __restrict__ x, size_t n, double* __restrict__ out) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) *out = v;
+    }
+}
+
+// ---------------------------------------------------------------- row sums of the Z part (K3)
+// rowsum[j] = sum_k gam[j][k] * W[j][k] + I0[j][k]; one warp per row, fixed summation order.
+__global__ void __launch_bounds__(256) rowsums_kernel(const double* __restrict__ gam, const double* __restrict__ wtab,
+                                                      const double* __restrict__ i0tab, int p, int q, int q_pad,
+                                                      double* __restrict__ rowsum) {
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= p) return;
+    const int lane = threadIdx.x & 31;
+    const size_t base = (size_t)j * q_pad;
+    double s0 = 0.0, s1 = 0.0;
+    const int q2 = q & ~1;
+    for (int k = 2 * lane; k < q2; k += 64) {
+        const double2 g = *reinterpret_cast<const double2*>(gam + base + k);
+        const double2 w = *reinterpret_cast<const double2*>(wtab + base + k);
+        const double2 i0 = *reinterpret_cast<const double2*>(i0tab + base + k);
+        s0 += fma(g.x, w.x, i0.x);
+        s1 += fma(g.y, w.y, i0.y);
+    }
+    if (lane == 0 && q2 < q) s0 += fma(gam[base + q2], wtab[base + q2], i0tab[base + q2]);
+    const double s = warp_sum(s0 + s1);
+    if (lane == 0) rowsum[j] = s;
+}
+
+}  // namespace aq

@@ -1,0 +1,113 @@
+"""`SweepContext`: Python face of one aq_ctx (one GPU, one slab of traits)."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+
+class SweepContext:
+    """Owns the device state of the CAVI sweep for q_local traits (include/atlasqtl_b200.h)."""
+
+    def __init__(self, X, Y, device=0):
+        self._lib = _lib.load()
+        X = _lib.fmat(X)
+        Y = _lib.fmat(Y)
+        if X.shape[0] != Y.shape[0]:
+            raise ValueError("X and Y must have the same number of rows")
+        self.n, self.p = X.shape
+        self.q = Y.shape[1]
+        self._ctx = ctypes.c_void_p()
+        _lib.check(self._lib.aq_create(ctypes.byref(self._ctx), ctypes.c_int(device), self.n, self.p, self.q,
+                                       _lib.dptr(X), _lib.dptr(Y)))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self._lib.aq_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def dims(self):
+        v = [ctypes.c_int() for _ in range(5)]
+        _lib.check(self._lib.aq_dims(self._ctx, *[ctypes.byref(x) for x in v]))
+        return dict(zip(("n", "p", "q", "p_pad", "q_pad"), (x.value for x in v)))
+
+    def set_order(self, shuffled_ind=None):
+        arr = None if shuffled_ind is None else np.ascontiguousarray(shuffled_ind, dtype=np.int32)
+        if arr is not None and arr.shape != (self.p,):
+            raise ValueError("shuffled_ind must have length p")
+        _lib.check(self._lib.aq_set_order(self._ctx, _lib.iptr(arr)))
+
+    def _qvecs(self, k):
+        return [np.empty(self.q) for _ in range(k)]
+
+    def set_state(self, gam_vb, mu_beta_vb):
+        g, m = _lib.fmat(gam_vb), _lib.fmat(mu_beta_vb)
+        if g.shape != (self.p, self.q) or m.shape != (self.p, self.q):
+            raise ValueError("gam_vb / mu_beta_vb must be p x q")
+        o = self._qvecs(4)
+        _lib.check(self._lib.aq_set_state(self._ctx, _lib.dptr(g), _lib.dptr(m), *[_lib.dptr(x) for x in o]))
+        return dict(colsum_gam=o[0], colsum_gam_mu2=o[1], colsum_beta2=o[2], resid_sq=o[3])
+
+    def get_state(self, gam=True, mu=True, beta=True):
+        outs = [np.empty((self.p, self.q), order="F") if f else None for f in (gam, mu, beta)]
+        _lib.check(self._lib.aq_get_state(self._ctx, *[_lib.dptr(x) for x in outs]))
+        return dict(gam_vb=outs[0], mu_beta_vb=outs[1], beta_vb=outs[2])
+
+    def get_residual(self):
+        r = np.empty((self.n, self.q), order="F")
+        _lib.check(self._lib.aq_get_residual(self._ctx, _lib.dptr(r)))
+        return r
+
+    def refresh_tables(self, theta_vb, zeta_vb, c_next=1.0, want_elbo=False):
+        th = np.ascontiguousarray(theta_vb, dtype=np.float64)
+        ze = np.ascontiguousarray(zeta_vb, dtype=np.float64)
+        if th.shape != (self.p,) or ze.shape != (self.q,):
+            raise ValueError("theta_vb must have length p and zeta_vb length q_local")
+        out = ctypes.c_double()
+        _lib.check(self._lib.aq_refresh_tables(self._ctx, _lib.dptr(th), _lib.dptr(ze), ctypes.c_double(c_next),
+                                               ctypes.byref(out) if want_elbo else None))
+        return out.value if want_elbo else None
+
+    def sweep(self, c, log_sig2_inv_vb, tau_vb, log_tau_vb, sig2_beta_vb):
+        vecs = [np.ascontiguousarray(v, dtype=np.float64) for v in (tau_vb, log_tau_vb, sig2_beta_vb)]
+        for v in vecs:
+            if v.shape != (self.q,):
+                raise ValueError("per-trait vectors must have length q_local")
+        o = self._qvecs(5)
+        _lib.check(self._lib.aq_sweep(self._ctx, ctypes.c_double(c), ctypes.c_double(log_sig2_inv_vb),
+                                      *[_lib.dptr(v) for v in vecs], *[_lib.dptr(x) for x in o]))
+        return dict(colsum_gam=o[0], colsum_gam_mu2=o[1], colsum_beta2=o[2], resid_sq=o[3], colsum_zpart=o[4])
+
+    def rowsums_zpart(self):
+        r = np.empty(self.p)
+        _lib.check(self._lib.aq_rowsums_zpart(self._ctx, _lib.dptr(r)))
+        return r
+
+    def rowsums_zpart_dev(self):
+        ptr = _lib._DP()
+        _lib.check(self._lib.aq_rowsums_zpart_dev(self._ctx, ctypes.byref(ptr)))
+        return ctypes.cast(ptr, ctypes.c_void_p).value
+
+    def launch_count(self):
+        return int(self._lib.aq_launch_count(self._ctx))
+
+    def last_sweep_ms(self):
+        ms = ctypes.c_float()
+        _lib.check(self._lib.aq_last_sweep_ms(self._ctx, ctypes.byref(ms)))
+        return ms.value
+
+    def sync(self):
+        _lib.check(self._lib.aq_sync(self._ctx))

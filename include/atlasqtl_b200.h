@@ -1,0 +1,153 @@
+/*
+ * atlasqtl_b200 -- C ABI of the B200-native CAVI sweep hot path of atlasqtl.
+ *
+ * This is the drop-in boundary for the reference's R <-> native interface of that path:
+ *
+ *   reference interface replaced                                   file:line (under /root/reference)
+ *   ------------------------------------------------------------   ---------------------------------
+ *   .Call `_atlasqtl_coreDualLoop` (15 SEXP args), R closure       src/RcppExports.cpp:17-38,
+ *       coreDualLoop(cp_X, cp_Y_X, gam_vb, log_Phi..., c)          R/RcppExports.R:4-6,
+ *       called once per VB iteration                               R/atlasqtl_global_local_core.R:167-170
+ *   the Gram / cross-product set-up that feeds it                  R/atlasqtl_global_local_core.R:40-42,112-115
+ *   the p x q / n x q reductions around it (update_nu/rho/eta/     R/update_vb.R:19-31,116-118,127-157,217-234
+ *       kappa_vb_, update_m2_beta_, update_Z_ row/col sums)
+ *   log_Phi / log_1_min_Phi tables                                 R/atlasqtl_global_local_core.R:61-63,293-295
+ *   ELBO term B (e_beta_gamma_)                                    R/elbo.R:10-34
+ *
+ * The reference's dual-form argument list (p x p Gram matrix) cannot exist at the sizes this library
+ * targets, so the state (X, residual Y - X beta, gam_vb, mu_beta_vb, tables) lives on the device
+ * between calls and the per-iteration entry points exchange only p-, q- and scalar-sized objects
+ * (SURVEY.md section 8b).  INTEGRATION.md shows the `.Call` shim and the patched R call site.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative AQ_E* code on failure; aq_last_error() gives
+ *     the message of the last failure on the calling thread.  No C++ exception or CUDA sticky error
+ *     crosses this boundary.
+ *   - all matrices are column-major double (R layout); index vectors are int32, 0-based, exactly as
+ *     the reference passes them (R/atlasqtl_global_local_core.R:162-163).
+ *   - pointers are HOST pointers unless the name ends in _dev.
+ *   - one context = one GPU = one contiguous slab of q_local traits (traits are independent inside
+ *     a sweep, src/coreLoop.cpp:58-85).  X is replicated per context.
+ *   - calls on one context must come from one host thread at a time; the library never calls back.
+ */
+#ifndef ATLASQTL_B200_H_
+#define ATLASQTL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AQ_OK 0
+#define AQ_EINVAL (-1)   /* bad argument (NULL, dimension, permutation out of range, ...) */
+#define AQ_ECUDA (-2)    /* CUDA runtime failure */
+#define AQ_ENOMEM (-3)   /* device allocation failed */
+#define AQ_ESTATE (-4)   /* call order violated (e.g. sweep before set_state / refresh_tables) */
+#define AQ_EUNSUPPORTED (-5) /* shape outside what this build of the kernels covers */
+
+typedef struct aq_ctx aq_ctx;
+
+const char* aq_last_error(void);
+int aq_version(void);
+
+/* Number of SMs, free / total bytes of the device; a cheap "is there a usable GPU" probe. */
+int aq_device_info(int device, int* sm_count, int64_t* free_bytes, int64_t* total_bytes);
+
+/*
+ * Create a context on `device` and upload the data.
+ *   X  n x p  standardised predictors (post-conditions of R/prepare_atlasqtl.R:57-72)
+ *   Y  n x q_local  centred responses of this slab (R/prepare_atlasqtl.R:83)
+ * Replaces cp_X <- crossprod(X); cp_Y_X <- crossprod(Y, X); Y_norm_sq (R/atlasqtl_global_local_core.R:40-42):
+ * the library keeps X (tiled in sweep order) and the residual instead.
+ */
+int aq_create(aq_ctx** out, int device, int n, int p, int q_local, const double* X, const double* Y);
+int aq_destroy(aq_ctx* ctx);
+
+/* Dimensions and padded leading dimensions of the device layout (for callers that pass _dev pointers). */
+int aq_dims(const aq_ctx* ctx, int* n, int* p, int* q_local, int* p_pad, int* q_pad);
+
+/*
+ * Visiting order of the SNPs for subsequent sweeps: shuffled_ind of coreDualLoop
+ * (src/coreLoop.cpp:64-65; the reference default is 0:(p-1), R/atlasqtl_global_local_core.R:162).
+ * Must be a permutation of 0..p-1.  NULL selects the identity.  Re-tiles X and its block Gram band
+ * when the order changes; a no-op otherwise.
+ */
+int aq_set_order(aq_ctx* ctx, const int32_t* shuffled_ind);
+
+/*
+ * Load the variational state gam_vb, mu_beta_vb (p x q_local) and derive beta_vb = gam_vb * mu_beta_vb
+ * and the residual Y - X beta_vb on the device (replaces update_beta_vb_, update_cp_X_Xbeta_,
+ * R/atlasqtl_global_local_core.R:112-115).  Also returns the per-trait sums of aq_sweep (any may be NULL).
+ */
+int aq_set_state(aq_ctx* ctx, const double* gam_vb, const double* mu_beta_vb,
+                 double* colsum_gam, double* colsum_gam_mu2, double* colsum_beta2, double* resid_sq);
+
+/* Copy the state back in R layout (any pointer may be NULL): the in-place outputs of coreDualLoop. */
+int aq_get_state(aq_ctx* ctx, double* gam_vb, double* mu_beta_vb, double* beta_vb);
+
+/* Residual Y - X beta_vb (n x q_local), mainly for tests: X'(Y - residual) is the reference's cp_betaX_X. */
+int aq_get_residual(aq_ctx* ctx, double* resid);
+
+/*
+ * Streaming p x q_local pass after theta_vb / zeta_vb changed
+ * (replaces R/atlasqtl_global_local_core.R:61-63 and :293-295):
+ *   D    = log(1 - Phi(theta_j + zeta_k)) - log Phi(theta_j + zeta_k)      (the only way the sweep uses the tables)
+ *   W    = imr1 - imr0,  I0 = imr0 at U = sqrt(c_next) (theta_j + zeta_k)  (inv_mills_ratio_, R/utils.R:172-191)
+ * c_next is the temperature of the NEXT sweep (its update_Z_ evaluates the CDFs at sqrt(c) (theta + zeta),
+ * R/update_vb.R:219-224).  If elbo_b_part != NULL it also returns the p x q part of ELBO term B
+ * (R/elbo.R:19-26):  sum_jk [ gam lp + (1-gam) lq - gam log(gam+eps) - (1-gam) log(1-gam+eps) ]
+ * with the post-update lp / lq and the current gam_vb.
+ */
+int aq_refresh_tables(aq_ctx* ctx, const double* theta_vb, const double* zeta_vb, double c_next,
+                      double* elbo_b_part);
+
+/*
+ * One Gauss-Seidel sweep over all SNPs x the slab's traits: coreDualLoop (src/coreLoop.cpp:38-86) in
+ * sample space, blocked over SNPs, in the order of aq_set_order.
+ *   in : c, log_sig2_inv_vb, and per-trait tau_vb, log_tau_vb, sig2_beta_vb (length q_local)
+ *   out (length q_local, any may be NULL), all evaluated on the post-sweep state:
+ *     colsum_gam      colSums(gam_vb)                               (update_eta_vb_, update_nu_vb_)
+ *     colsum_gam_mu2  colSums(gam_vb * mu_beta_vb^2); colSums(m2_beta) = this + sig2_beta_vb * colsum_gam
+ *     colsum_beta2    colSums(beta_vb^2)                            (update_kappa_vb_)
+ *     resid_sq        colSums((Y - X beta_vb)^2) = Y_norm_sq - 2 colSums(beta*t(cp_Y_X)) + colSums(cp_X_Xbeta*beta)
+ *     colsum_zpart    sum_j [gam_jk W_jk + I0_jk]; colSums(Z)_k = colsum_zpart_k / sqrt(c) + sum(theta) + p zeta_k
+ */
+int aq_sweep(aq_ctx* ctx, double c, double log_sig2_inv_vb, const double* tau_vb, const double* log_tau_vb,
+             const double* sig2_beta_vb, double* colsum_gam, double* colsum_gam_mu2, double* colsum_beta2,
+             double* resid_sq, double* colsum_zpart);
+
+/*
+ * rowsum_zpart_j = sum_k [gam_jk W_jk + I0_jk] over this slab (length p);
+ * rowSums(Z)_j = (sum over slabs) / sqrt(c) + q theta_j + sum(zeta)   (update_theta_vb_, R/update_vb.R:179).
+ * The _dev variant leaves the result in device memory (length p_pad doubles, first p valid) so that the
+ * caller can all-reduce it across slabs (NCCL) without a host round trip.
+ */
+int aq_rowsums_zpart(aq_ctx* ctx, double* rowsum_zpart);
+int aq_rowsums_zpart_dev(aq_ctx* ctx, double** rowsum_zpart_dev);
+
+/* Count of kernel launches issued through this context so far (bench.py's gpu_launches). */
+int64_t aq_launch_count(const aq_ctx* ctx);
+
+/* Device time of the last aq_sweep's main kernel in milliseconds (CUDA events on the context's stream). */
+int aq_last_sweep_ms(const aq_ctx* ctx, float* ms);
+
+/* Block until everything queued on the context's stream has finished. */
+int aq_sync(aq_ctx* ctx);
+
+/*
+ * Drop-in for the reference's stateless entry point at sizes where its p x p inputs exist:
+ * same 15 arguments, same in-place outputs (gam_vb, m1_beta, cp_betaX_X, mu_beta_vb) as
+ * coreDualLoop (src/coreLoop.cpp:38-52), plus the dimensions an R matrix carries in its dim attribute.
+ * Needs X'X = cp_X to be factorised on every call, so it is a compatibility / parity entry, not the fast path.
+ */
+int aq_coreDualLoop(int device, int p, int q, const double* cp_X, const double* cp_Y_X, double* gam_vb,
+                    const double* log_Phi_theta_plus_zeta, const double* log_1_min_Phi_theta_plus_zeta,
+                    double log_sig2_inv_vb, const double* log_tau_vb, double* m1_beta, double* cp_betaX_X,
+                    double* mu_beta_vb, const double* sig2_beta_vb, const double* tau_vb,
+                    const int32_t* shuffled_ind, int n_ind, const int32_t* sample_q, int n_q, double c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATLASQTL_B200_H_ */
