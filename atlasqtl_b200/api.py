@@ -1,0 +1,60 @@
+"""`atlasqtl()`: the reference's user entry point (R/atlasqtl.R:179-322) on top of the CUDA hot path.
+
+Same arguments, same output object (a dict with the fields of the R list, R/atlasqtl_global_local_core.R:414-428
+plus p0 / rmvd_cst_x / rmvd_coll_x, R/atlasqtl.R:293-314).  Extra keyword-only arguments select the GPU
+and, under torch.distributed, the slab of traits this process owns.
+"""
+import numpy as np
+
+from . import core, hyper_init, prepare
+
+
+def atlasqtl(Y, X, p0, anneal=(1, 2, 10), tol=0.1, maxit=1000, user_seed=None, verbose=1, list_hyper=None,
+             list_init=None, save_hyper=False, save_init=False, full_output=False, thinned_elbo_eval=True,
+             checkpoint_path=None, trace_path=None, add_collinear_back=False, *, device=0, comm=None, order_fn=None,
+             trace=None, context_factory=None):
+    if verbose not in (0, 1, 2):
+        raise ValueError("The verbose argument must be set to 0, 1 or 2.")
+    core.check_annealing_(anneal)
+    dat = prepare.prepare_data_(Y, X, tol, maxit, user_seed, verbose)
+    Xp, Yp = dat["X"], dat["Y"]
+    n, p = Xp.shape
+    q = Yp.shape[1]
+    shr_fac_inv = q  # R/atlasqtl.R:218
+    if list_hyper is None or list_init is None:
+        if p0 is None or len(p0) != 2 or min(p0) <= 0:
+            raise ValueError("p0 must be a vector of two positive numbers.")
+    if list_hyper is None:
+        list_hyper = hyper_init.auto_set_hyper_(Yp, p, p0)
+    elif list_hyper["p_hyper"] != p or list_hyper["q_hyper"] != q:
+        raise ValueError("The dimensions of list_hyper do not match those of the (pre-processed) data.")
+    if list_init is None:
+        list_init = hyper_init.auto_set_init_(Yp, p, p0, shr_fac_inv, user_seed)
+    elif list_init["p_init"] != p or list_init["q_init"] != q:
+        raise ValueError("The dimensions of list_init do not match those of the (pre-processed) data.")
+    if add_collinear_back:
+        raise NotImplementedError("add_collinear_back is host-side post-processing outside this path")
+
+    df = 1  # R/atlasqtl.R:272 (hs <- TRUE, debug <- TRUE)
+    slab = None
+    Y_loc = Yp
+    if comm is not None and comm.world_size > 1:
+        from .dist import slab_bounds
+        slab = slab_bounds(q, comm.rank, comm.world_size)
+        Y_loc = np.asfortranarray(Yp[:, slab[0]:slab[1]])
+    res = core.atlasqtl_global_local_core_(Y_loc, Xp, shr_fac_inv, anneal, df, tol, maxit, verbose, list_hyper,
+                                           list_init, checkpoint_path, trace_path, full_output, thinned_elbo_eval,
+                                           debug=True, comm=comm, slab=slab, device=device, order_fn=order_fn,
+                                           trace=trace, context_factory=context_factory)
+    if comm is not None and comm.world_size > 1:
+        res = comm.gather_result(res, q)
+    res["p0"] = p0
+    res["rmvd_cst_x"] = dat["rmvd_cst_x"]
+    res["rmvd_coll_x"] = dat["rmvd_coll_x"]
+    res["names_x"], res["names_y"] = dat["names_x"], dat["names_y"]
+    if save_hyper:
+        res["list_hyper"] = list_hyper
+    if save_init:
+        res["list_init"] = list_init
+    res["_class"] = "atlasqtl"
+    return res

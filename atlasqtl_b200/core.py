@@ -1,0 +1,348 @@
+"""VB outer loop of the global-local (horseshoe) model: host-side mirror of
+`atlasqtl_global_local_core_` (reference R/atlasqtl_global_local_core.R:8-433) driving the CUDA
+sweep through the C ABI.
+
+What moved to the device (include/atlasqtl_b200.h) and what stays here:
+
+  device  step 10 (coreDualLoop), m2_beta / Z / log-CDF tables (steps 11, 12, 19), every p x q and
+          n x q reduction (steps 1-5, 16, 18) and the p x q part of ELBO term B;
+  host    the p-, q- and scalar-sized algebra between those calls -- the same statements as
+          R/atlasqtl_global_local_core.R:134-150, :241-290, :318-375 and R/elbo.R, written against
+          the per-trait / per-SNP sums the device hands back.
+
+Traits are independent inside a sweep, so several processes can each own a slab of traits
+(`slab`): the only cross-slab quantities are rowSums(Z) (p), a few scalars per sweep and the ELBO
+partial sums; they go through `comm.allreduce_sum` (NCCL via torch.distributed, see dist.py).
+"""
+import math
+
+import numpy as np
+from scipy import special as sp
+
+from .device import SweepContext
+
+ALL_EQUAL_TOL = 1.5e-8  # isTRUE(all.equal(c, 1))
+
+
+class SerialComm:
+    """Single-slab stand-in for dist.TorchComm."""
+    rank, world_size = 0, 1
+
+    def allreduce_sum(self, x):
+        return x
+
+
+# ----------------------------------------------------------------------------- small host helpers
+def get_annealing_ladder_(anneal):
+    """R/utils.R:108-146."""
+    k_m = 1.0 / anneal[1]
+    m = int(anneal[2])
+    down = np.arange(m, 0, -1, dtype=np.float64)
+    if anneal[0] == 1:
+        return (1 + (k_m ** (1.0 / (1 - m)) - 1)) ** (1 - down)
+    if anneal[0] == 2:
+        return 1 / (1 + ((1 / k_m - 1) / (m - 1)) * (down - 1))
+    return k_m + ((1 - k_m) / (m - 1)) * (np.arange(1, m + 1, dtype=np.float64) - 1)
+
+
+def check_annealing_(anneal):
+    """R/prepare_atlasqtl.R:100-124."""
+    if anneal is None:
+        return
+    if len(anneal) != 3:
+        raise ValueError("anneal must be NULL/None or a vector of length 3.")
+    if anneal[0] not in (1, 2, 3):
+        raise ValueError("The annealing spacing scheme must be set to 1 for geometric 2 for harmonic or 3 for "
+                         "linear spacing.")
+    if anneal[1] < 1.5:
+        raise ValueError("Initial annealing temperature very small. May not be large enough for a successful "
+                         "exploration. Please increase it or select no annealing.")
+    if anneal[2] > 1000 or anneal[2] != int(anneal[2]) or anneal[2] < 1:
+        raise ValueError("Temperature grid size must be a natural number <= 1000.")
+
+
+def Q_approx_vec(x, eps1=1e-30, eps2=1e-7):
+    """E1(x) exp(x): gsl::expint_E1 branch for x <= 1, modified Lentz for x > 1 with the reference's
+    vector-wide stopping rule (R/utils.R:380-423)."""
+    x = np.asarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    lo = x <= 1
+    out[lo] = sp.exp1(x[lo]) * np.exp(x[lo])
+    if (~lo).any():
+        xu = x[~lo]
+        f_p = np.full_like(xu, eps1)
+        C_p = np.full_like(xu, eps1)
+        D_p = np.zeros_like(xu)
+        Delta = np.full_like(xu, 2 + eps2)
+        j = 1
+        while np.max(np.abs(Delta - 1)) >= eps2:
+            j += 1
+            D_c = 1 / (xu + 2 * j - 1 - ((j - 1) ** 2) * D_p)
+            C_c = xu + 2 * j - 1 - ((j - 1) ** 2) / C_p
+            Delta = C_c * D_c
+            f_p = f_p * Delta
+            C_p, D_p = C_c, D_c
+        out[~lo] = 1 / (xu + 1 + f_p)
+    return out
+
+
+def _upper_gamma(a, x):
+    return sp.gamma(a) * sp.gammaincc(a, x)  # gsl::gamma_inc(a, x), a > 0 on this path
+
+
+def update_annealed_lam2_inv_vb_(L_vb, c, df):
+    if df != 1:
+        raise NotImplementedError("df is fixed to 1 by the reference (R/atlasqtl.R:272)")
+    return _upper_gamma(2 - c, L_vb) / (_upper_gamma(1 - c, L_vb) * L_vb) - 1  # R/update_vb.R:74
+
+
+def _e_sig2_inv(nu, nu_vb, log_sig2_inv_vb, rho, rho_vb, sig2_inv_vb):
+    return ((nu - nu_vb) * log_sig2_inv_vb - (rho - rho_vb) * sig2_inv_vb + nu * math.log(rho)
+            - nu_vb * math.log(rho_vb) - sp.gammaln(nu) + sp.gammaln(nu_vb))  # R/elbo.R:41-46
+
+
+# ----------------------------------------------------------------------------- the core
+def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbose, list_hyper, list_init,
+                                checkpoint_path=None, trace_path=None, full_output=False,
+                                thinned_elbo_eval=True, debug=False, batch="y", *, comm=None, slab=None,
+                                device=0, context_factory=None, order_fn=None, trace=None, ctx=None):
+    """Same positional arguments as the reference core (R/atlasqtl_global_local_core.R:8-13).
+
+    Y is THIS process's slab of responses (all of Y when comm is None); `slab` = (k_first, k_last)
+    gives its position among the q_total = shr_fac_inv traits so that per-trait hyper / init vectors
+    (length q_total) can be sliced.  `order_fn(it, p)` supplies shuffled_ind per iteration (identity
+    by default, like the reference, :162).  Keyword-only arguments are extensions; the R-facing ones
+    keep their meaning.  Missing values in Y (coreDualMisLoop) are not supported by this build.
+    """
+    if batch != "y":
+        raise ValueError("Batch scheme not defined. Exit.")  # only the C++ path is replaced (:179-232)
+    if np.isnan(Y).any():
+        raise NotImplementedError("missing responses (coreDualMisLoop) are not covered by this build")
+    if checkpoint_path is not None or trace_path is not None:
+        raise NotImplementedError("checkpoint_path / trace_path are host-side I/O outside this path")
+    comm = comm or SerialComm()
+    n, q = Y.shape
+    p = X.shape[1]
+    q_total = int(shr_fac_inv)
+    k_first, k_last = slab if slab is not None else (0, q)
+    if k_last - k_first != q:
+        raise ValueError("slab does not match the number of columns of Y")
+    sl = slice(k_first, k_last)
+
+    def per_trait(v):
+        v = np.asarray(v, dtype=np.float64)
+        return v[sl].copy() if v.shape == (q_total,) else np.full(q, float(v))
+
+    h = list_hyper
+    eta, kappa, n0 = per_trait(h["eta"]), per_trait(h["kappa"]), per_trait(h["n0"])
+    nu, rho, t02 = float(h["nu"]), float(h["rho"]), float(h["t02"])
+    m0, A2_inv = float(h.get("m0", 0.0)), float(h.get("A2_inv", 1.0))
+
+    gam0 = np.asarray(list_init["gam_vb"])
+    mu0 = np.asarray(list_init["mu_beta_vb"])
+    if gam0.shape[1] == q_total and q_total != q:
+        gam0, mu0 = gam0[:, sl], mu0[:, sl]
+    sig02_inv_vb = float(list_init["sig02_inv_vb"])
+    sig2_beta_vb = per_trait(list_init["sig2_beta_vb"])
+    sig2_theta_vb = np.array(list_init["sig2_theta_vb"], dtype=np.float64)
+    tau_vb = per_trait(list_init["tau_vb"])
+    theta_vb = np.array(list_init["theta_vb"], dtype=np.float64)
+    zeta_vb = per_trait(list_init["zeta_vb"])
+
+    anneal_scale = True  # :71
+    if anneal is None:
+        annealing, c, c_s, it_init, ladder = False, 1.0, 1.0, 1, None
+    else:
+        annealing = True
+        ladder = get_annealing_ladder_(anneal)
+        c = float(ladder[0])
+        c_s = c if anneal_scale else 1.0
+        it_init = int(anneal[2])
+    eps = np.finfo(np.float64).eps ** 0.5  # :85
+    if thinned_elbo_eval:
+        times_conv_sched, batch_conv_sched = np.array([1.0, 5.0, 10.0, 50.0]), [1, 10, 25, 50]
+    else:
+        times_conv_sched, batch_conv_sched = np.array([1.0]), [1]
+    ind_batch_conv = len(batch_conv_sched) + 1
+    batch_conv = 1
+
+    t02_inv = 1 / t02
+    sig2_zeta_vb = 1 / (c * (p + t02_inv))  # update_sig2_c0_vb_(p, t02, c), :105
+    vec_sum_log_det_zeta = -q_total * (math.log(t02) + math.log(p + t02_inv))  # :107
+    nu_xi_inv_vb = 1.0  # :119
+
+    own_ctx = ctx is None
+    if own_ctx:
+        factory = context_factory or (lambda X_, Y_: SweepContext(X_, Y_, device=device))
+        ctx = factory(X, Y)
+    try:
+        order = None
+        if order_fn is not None:
+            order = np.ascontiguousarray(order_fn(1, p), dtype=np.int32)
+        ctx.set_order(order)
+        sums = ctx.set_state(gam0, mu0)  # beta_vb, residual, and the sums m2_beta / kappa_vb need (:112-115)
+        del gam0, mu0
+        ctx.refresh_tables(theta_vb, zeta_vb, c_next=c)  # :61-63
+        sig2_beta_for_m2 = sig2_beta_vb  # m2_beta always pairs gam/mu with the sig2_beta_vb of their sweep (:113,:235)
+        glob = comm.allreduce_sum(np.array([sums["colsum_gam"].sum(),
+                                            np.dot(tau_vb, sums["colsum_gam_mu2"] + sig2_beta_for_m2 * sums["colsum_gam"]),
+                                            zeta_vb.sum()]))
+        sum_gam, tau_dot_m2, sum_zeta = (float(v) for v in glob)
+
+        converged = False
+        lb_new = lb_old = -np.inf
+        it = 0
+        Q_app = None
+        lam2_inv_vb = None
+
+        while (not converged) and (it < maxit):
+            lb_old = lb_new
+            it += 1
+            if verbose != 0 and comm.rank == 0 and (it == 1 or it % max(5, batch_conv) == 0):
+                print(f"Iteration {it}... ")
+
+            colsum_m2 = sums["colsum_gam_mu2"] + sig2_beta_for_m2 * sums["colsum_gam"]
+            nu_vb = c * (nu + sum_gam / 2) - c + 1  # :134
+            rho_vb = c * (rho + tau_dot_m2 / 2)  # :135 (uses the tau_vb of the previous iteration)
+            sig2_inv_vb = nu_vb / rho_vb  # :137
+            eta_vb = c * (eta + n / 2 + sums["colsum_gam"] / 2) - c + 1  # :141
+            kappa_vb = c * (kappa + (sums["resid_sq"] + (n - 1 + sig2_inv_vb) * colsum_m2
+                                     - (n - 1) * sums["colsum_beta2"]) / 2)  # :142, R/update_vb.R:144-146
+            tau_vb = eta_vb / kappa_vb  # :145
+            sig2_beta_vb = 1 / (c * (n - 1 + sig2_inv_vb) * tau_vb)  # :147
+            log_tau_vb = sp.digamma(eta_vb) - np.log(kappa_vb)  # :149
+            log_sig2_inv_vb = float(sp.digamma(nu_vb) - math.log(rho_vb))  # :150
+
+            if order_fn is not None and it > 1:
+                ctx.set_order(np.ascontiguousarray(order_fn(it, p), dtype=np.int32))  # :160-163
+
+            # ---- the sweep (:167-170) with the fused reductions
+            sums = ctx.sweep(c, log_sig2_inv_vb, tau_vb, log_tau_vb, sig2_beta_vb)
+            sig2_beta_for_m2 = sig2_beta_vb
+            colsum_m2 = sums["colsum_gam_mu2"] + sig2_beta_vb * sums["colsum_gam"]  # :235
+            rows = ctx.rowsums_zpart()
+            glob = comm.allreduce_sum(np.concatenate([rows, [sums["colsum_gam"].sum(), np.dot(tau_vb, colsum_m2)]]))
+            rowsum_zpart, sum_gam, tau_dot_m2 = glob[:p], float(glob[p]), float(glob[p + 1])
+
+            sqrt_c = 1.0 if abs(c - 1) < ALL_EQUAL_TOL else math.sqrt(c)  # R/update_vb.R:219-229
+            rowsums_Z = rowsum_zpart / sqrt_c + q_total * theta_vb + sum_zeta  # :237
+            colsums_Z = sums["colsum_zpart"] / sqrt_c + theta_vb.sum() + p * zeta_vb
+
+            th2 = theta_vb ** 2 + sig2_theta_vb - 2 * theta_vb * m0 + m0 ** 2
+            L_vb = c_s * sig02_inv_vb * shr_fac_inv * th2 / 2 / df  # :241
+            rho_xi_inv_vb = c_s * (A2_inv + sig02_inv_vb)  # :242
+            if annealing and anneal_scale:
+                lam2_inv_vb = update_annealed_lam2_inv_vb_(L_vb, c_s, df)  # :246
+            else:
+                Q_app = Q_approx_vec(L_vb)  # :250
+                lam2_inv_vb = 1 / (Q_app * L_vb) - 1  # :254
+            xi_inv_vb = nu_xi_inv_vb / rho_xi_inv_vb  # :276
+            prior_prec = sig02_inv_vb * lam2_inv_vb * shr_fac_inv
+            sig2_theta_vb = 1 / (c * (q_total + prior_prec))  # :278
+            theta_vb = c * sig2_theta_vb * (rowsums_Z + prior_prec * m0 - sum_zeta)  # :280
+            nu_s0_vb = c_s * (0.5 + p / 2) - c_s + 1  # :283
+            rho_s0_vb = c_s * (xi_inv_vb + np.sum(lam2_inv_vb * shr_fac_inv * (
+                theta_vb ** 2 + sig2_theta_vb - 2 * theta_vb * m0 + m0 ** 2)) / 2)  # :285
+            sig02_inv_vb = float(nu_s0_vb / rho_s0_vb)  # :288
+            zeta_vb = c * sig2_zeta_vb * (colsums_Z + t02_inv * n0 - theta_vb.sum())  # :290
+
+            rec = dict(it=it, c=c, annealing=annealing, lb=None, sig2_inv_vb=sig2_inv_vb, sig02_inv_vb=sig02_inv_vb,
+                       sum_gam=sum_gam, sweep_ms=getattr(ctx, "last_sweep_ms", lambda: float("nan"))())
+            c_prev = c
+            want_elbo = False
+            if annealing:  # :318-336
+                sig2_zeta_vb = c * sig2_zeta_vb
+                c = float(ladder[it]) if it < len(ladder) else 1.0
+                c_s = c if anneal_scale else 1.0
+                sig2_zeta_vb = sig2_zeta_vb / c
+                if abs(c - 1) < ALL_EQUAL_TOL:
+                    annealing = False
+                    if verbose != 0 and comm.rank == 0:
+                        print("** Exiting annealing mode. **\n")
+            else:
+                want_elbo = it <= it_init + 1 or it % batch_conv == 0 or it % batch_conv == 1  # :342
+
+            # theta / zeta changed: refresh D, W, I0 for the next sweep (:293-295), ELBO-B part on demand
+            elbo_b_dev = ctx.refresh_tables(theta_vb, zeta_vb, c_next=c, want_elbo=want_elbo)
+            sum_zeta_local = zeta_vb.sum()
+
+            if want_elbo:
+                # ---- elbo_global_local_ (:440-495): c = 1 re-derivations from the post-sweep sums (:456-467)
+                eta_e = eta + n / 2 + sums["colsum_gam"] / 2
+                kappa_e = kappa + (sums["resid_sq"] + (n - 1 + sig2_inv_vb) * colsum_m2
+                                   - (n - 1) * sums["colsum_beta2"]) / 2
+                nu_e = nu + sum_gam / 2
+                rho_e = rho + tau_dot_m2 / 2
+                log_tau_e = sp.digamma(eta_e) - np.log(kappa_e)
+                log_sig2_inv_e = float(sp.digamma(nu_e) - math.log(rho_e))
+                log_sig02_inv_vb = float(sp.digamma(nu_s0_vb) - math.log(rho_s0_vb))
+                log_xi_inv_vb = float(sp.digamma(nu_xi_inv_vb) - math.log(rho_xi_inv_vb))
+                # A: e_y_ (R/elbo.R:135-146)
+                A = np.sum(-n / 2 * math.log(2 * math.pi) + n / 2 * log_tau_e
+                           - tau_vb * (kappa_e - colsum_m2 * sig2_inv_vb / 2 - kappa))
+                # B: e_beta_gamma_ (R/elbo.R:10-34): per-trait terms from the column sums + the device part
+                B_loc = (np.sum(sums["colsum_gam"] * (log_sig2_inv_e / 2 + log_tau_e / 2 + (np.log(sig2_beta_vb) + 1) / 2))
+                         - np.sum(colsum_m2 * tau_vb) * sig2_inv_vb / 2 + elbo_b_dev - p * q * sig2_zeta_vb / 2
+                         - q * np.sum(sig2_theta_vb) / 2)
+                # D: e_zeta_ without its constants (R/elbo.R:153-161);  E: e_tau_ (:63-68)
+                D_loc = -t02_inv * np.sum((zeta_vb - n0) ** 2) / 2
+                E = np.sum((eta - eta_e) * log_tau_e - (kappa - kappa_e) * tau_vb + eta * np.log(kappa)
+                           - eta_e * np.log(kappa_e) - sp.gammaln(eta) + sp.gammaln(eta_e))
+                tot = comm.allreduce_sum(np.array([A + B_loc + D_loc + E, sum_zeta_local]))
+                sum_zeta = float(tot[1])
+                D_cst = (vec_sum_log_det_zeta - q_total * t02_inv * sig2_zeta_vb + q_total) / 2
+                # C: e_theta_hs_, df = 1 (R/elbo.R:88-92)
+                C = float(np.sum((log_sig02_inv_vb + math.log(shr_fac_inv)) / 2
+                                 - sig02_inv_vb * shr_fac_inv * lam2_inv_vb
+                                 * (theta_vb ** 2 + sig2_theta_vb - 2 * m0 * theta_vb + m0 ** 2) / 2
+                                 + (np.log(sig2_theta_vb) + 1) / 2 - math.log(math.pi) + L_vb * lam2_inv_vb
+                                 + np.log(Q_app)))
+                F = (-0.5 * log_sig02_inv_vb - xi_inv_vb * sig02_inv_vb + log_xi_inv_vb / 2 - sp.gammaln(0.5)
+                     - (nu_s0_vb - 1) * log_sig02_inv_vb + rho_s0_vb * sig02_inv_vb
+                     - nu_s0_vb * math.log(rho_s0_vb) + sp.gammaln(nu_s0_vb))  # R/elbo.R:49-56
+                G = _e_sig2_inv(0.5, nu_xi_inv_vb, log_xi_inv_vb, A2_inv, rho_xi_inv_vb, xi_inv_vb)
+                H = _e_sig2_inv(nu, nu_e, log_sig2_inv_e, rho, rho_e, sig2_inv_vb)
+                lb_new = float(tot[0] + D_cst + C + F + G + H)
+                rec["lb"] = lb_new
+                if verbose != 0 and comm.rank == 0 and (it == it_init or it % max(5, batch_conv) == 0):
+                    print(f"ELBO = {lb_new}\n")
+                if debug and lb_new + eps < lb_old:  # :359-360
+                    raise RuntimeError("ELBO not increasing monotonically. Exit. ")
+                diff_lb = abs(lb_new - lb_old)
+                sum_exceed = int(np.sum(diff_lb > times_conv_sched * tol))  # :364
+                if sum_exceed == 0:
+                    converged = True
+                elif ind_batch_conv > sum_exceed:
+                    ind_batch_conv = sum_exceed
+                    batch_conv = batch_conv_sched[ind_batch_conv - 1]
+            else:
+                sum_zeta = float(comm.allreduce_sum(np.array([sum_zeta_local]))[0])
+            if trace is not None:
+                rec["c_next"] = c
+                rec["c"] = c_prev
+                trace.append(rec)
+
+        if verbose != 0 and comm.rank == 0:
+            if converged:
+                print(f"Convergence obtained after {it} iterations. \nOptimal marginal log-likelihood variational "
+                      f"lower bound (ELBO) = {lb_new}. \n")
+            else:
+                import warnings
+                warnings.warn("Maximal number of iterations reached before convergence. Exit.")
+
+        lb_opt = lb_new
+        st = ctx.get_state(gam=True, mu=bool(full_output), beta=True)
+        out = dict(beta_vb=st["beta_vb"], gam_vb=st["gam_vb"], theta_vb=theta_vb, zeta_vb=zeta_vb, n=n, p=p, q=q,
+                   anneal=anneal, converged=converged, it=it, maxit=maxit, tol=tol, lb_opt=lb_opt,
+                   diff_lb=abs(lb_opt - lb_old))  # :414-428
+        if full_output:  # :404-410 (no Gram objects exist in sample space)
+            out.update(mu_beta_vb=st["mu_beta_vb"], eta_vb=eta_vb, kappa_vb=kappa_vb, lam2_inv_vb=lam2_inv_vb,
+                       nu_s0_vb=nu_s0_vb, nu_vb=nu_vb, nu_xi_inv_vb=nu_xi_inv_vb, rho_s0_vb=rho_s0_vb, rho_vb=rho_vb,
+                       rho_xi_inv_vb=rho_xi_inv_vb, shr_fac_inv=shr_fac_inv, sig02_inv_vb=sig02_inv_vb,
+                       sig2_beta_vb=sig2_beta_vb, sig2_inv_vb=sig2_inv_vb, sig2_theta_vb=sig2_theta_vb,
+                       sig2_zeta_vb=sig2_zeta_vb, tau_vb=tau_vb, xi_inv_vb=xi_inv_vb, cp_Y_X=None, cp_X=None,
+                       cp_X_Xbeta=None)
+        return out
+    finally:
+        if own_ctx:
+            ctx.close()

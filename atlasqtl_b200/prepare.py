@@ -1,0 +1,63 @@
+"""Pre-processing: host-side mirror of `prepare_data_` (reference R/prepare_atlasqtl.R:8-88).
+
+One-off O(np) work that establishes the kernel's pre-conditions: columns of X centred and scaled with
+the n-1 standard deviation (so X_j'X_j = n-1), constant and duplicated columns dropped, Y centred.
+"""
+import numpy as np
+
+
+def rm_constant_(X_scaled, names):
+    """R/utils.R:276-300: columns that became NaN after scale() were constant."""
+    bool_cst = np.isnan(X_scaled).any(axis=0)
+    rmvd = [names[j] for j in np.flatnonzero(bool_cst)]
+    return X_scaled[:, ~bool_cst], bool_cst, rmvd
+
+
+def rm_collinear_(X_scaled, names):
+    """R/utils.R:303-343: drop exact duplicates (keep the first), remember who was dropped in favour of whom."""
+    seen = {}
+    bool_coll = np.zeros(X_scaled.shape[1], dtype=bool)
+    rmvd = {}
+    for j in range(X_scaled.shape[1]):
+        key = X_scaled[:, j].tobytes()
+        if key in seen:
+            bool_coll[j] = True
+            rmvd.setdefault(names[seen[key]], []).append(names[j])
+        else:
+            seen[key] = j
+    return X_scaled[:, ~bool_coll], bool_coll, rmvd
+
+
+def prepare_data_(Y, X, tol, maxit, user_seed=None, verbose=0):
+    """Returns dict(Y, X, bool_rmvd_x, initial_colnames_X, rmvd_cst_x, rmvd_coll_x, names_x, names_y)."""
+    X = np.asarray(X, dtype=np.float64)
+    Y = np.asarray(Y, dtype=np.float64)
+    if X.ndim != 2 or Y.ndim != 2:
+        raise ValueError("X and Y must be matrices.")
+    n, p = X.shape
+    if n < 2:
+        raise ValueError("X must have at least 2 rows.")  # check_structure_/check dims, :11-30
+    if Y.shape[0] != n:
+        raise ValueError("X and Y must have the same number of samples.")
+    if np.isnan(X).any():
+        raise ValueError("X must not contain missing values.")
+    if not (tol > 0):
+        raise ValueError("tol must be positive.")
+    if not (maxit >= 1 and int(maxit) == maxit):
+        raise ValueError("maxit must be a natural number.")
+    names_x = [f"Cov_x_{j + 1}" for j in range(p)]  # :54
+    names_y = [f"Resp_{k + 1}" for k in range(Y.shape[1])]  # :55
+    with np.errstate(invalid="ignore", divide="ignore"):
+        Xs = (X - X.mean(axis=0)) / X.std(axis=0, ddof=1)  # scale(X), :57
+    Xs, bool_cst, rmvd_cst = rm_constant_(Xs, names_x)
+    names_after_cst = [nm for nm, b in zip(names_x, bool_cst) if not b]
+    Xs, bool_coll, rmvd_coll = rm_collinear_(Xs, names_after_cst)
+    bool_rmvd = bool_cst.copy()
+    bool_rmvd[~bool_cst] = bool_coll  # :68-69
+    if Xs.shape[1] < 1:
+        raise ValueError("There must be at least 1 non-constant candidate predictor stored in X.")
+    Yc = Y - np.nanmean(Y, axis=0)  # scale(Y, center = TRUE, scale = FALSE), :83
+    kept = [nm for nm, b in zip(names_after_cst, bool_coll) if not b]
+    return dict(Y=np.asfortranarray(Yc), X=np.asfortranarray(Xs), bool_rmvd_x=bool_rmvd,
+                initial_colnames_X=names_after_cst, rmvd_cst_x=rmvd_cst, rmvd_coll_x=rmvd_coll, names_x=kept,
+                names_y=names_y)
