@@ -105,7 +105,7 @@ def _e_sig2_inv(nu, nu_vb, log_sig2_inv_vb, rho, rho_vb, sig2_inv_vb):
 def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbose, list_hyper, list_init,
                                 checkpoint_path=None, trace_path=None, full_output=False,
                                 thinned_elbo_eval=True, debug=False, batch="y", *, comm=None, slab=None,
-                                device=0, context_factory=None, order_fn=None, trace=None, ctx=None):
+                                device=0, context_factory=None, order_fn=None, trace=None, ctx=None, iter_hook=None):
     """Same positional arguments as the reference core (R/atlasqtl_global_local_core.R:8-13).
 
     Y is THIS process's slab of responses (all of Y when comm is None); `slab` = (k_first, k_last)
@@ -198,6 +198,8 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
         while (not converged) and (it < maxit):
             lb_old = lb_new
             it += 1
+            if iter_hook is not None:
+                iter_hook(it, ctx)
             if verbose != 0 and comm.rank == 0 and (it == 1 or it % max(5, batch_conv) == 0):
                 print(f"Iteration {it}... ")
 
@@ -248,6 +250,8 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
 
             rec = dict(it=it, c=c, annealing=annealing, lb=None, sig2_inv_vb=sig2_inv_vb, sig02_inv_vb=sig02_inv_vb,
                        sum_gam=sum_gam, sweep_ms=getattr(ctx, "last_sweep_ms", lambda: float("nan"))())
+            if hasattr(ctx, "last_ms"):
+                rec["rows_ms"] = ctx.last_ms(1)
             c_prev = c
             want_elbo = False
             if annealing:  # :318-336
@@ -265,6 +269,8 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
             # theta / zeta changed: refresh D, W, I0 for the next sweep (:293-295), ELBO-B part on demand
             elbo_b_dev = ctx.refresh_tables(theta_vb, zeta_vb, c_next=c, want_elbo=want_elbo)
             sum_zeta_local = zeta_vb.sum()
+            if hasattr(ctx, "last_ms"):
+                rec["tables_ms"] = ctx.last_ms(2)
 
             if want_elbo:
                 # ---- elbo_global_local_ (:440-495): c = 1 re-derivations from the post-sweep sums (:456-467)
@@ -322,6 +328,8 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
                 rec["c"] = c_prev
                 trace.append(rec)
 
+        if iter_hook is not None:
+            iter_hook(it + 1, ctx)
         if verbose != 0 and comm.rank == 0:
             if converged:
                 print(f"Convergence obtained after {it} iterations. \nOptimal marginal log-likelihood variational "

@@ -66,7 +66,9 @@ struct aq_ctx {
     int p_pad = 0, q_pad = 0, nb = 0, ntiles = 0, sm_count = 0;
     CfgInfo cfg{};
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // sweep kernel
+    cudaEvent_t evr0 = nullptr, evr1 = nullptr, evt0 = nullptr, evt1 = nullptr;  // rowsums / tables kernels
+    float last_rows_ms = 0.f, last_tables_ms = 0.f;
     double *xraw = nullptr, *xtiles = nullptr, *ymat = nullptr, *resid = nullptr;
     double *gam = nullptr, *mu = nullptr, *dtab = nullptr, *wtab = nullptr, *i0tab = nullptr;
     double *tvec = nullptr;     // 3 x q_pad: tau, log_tau, sig2_beta
@@ -222,6 +224,8 @@ int aq_destroy(aq_ctx* c) {
     if (c->order_dev) cudaFree(c->order_dev);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    for (cudaEvent_t e : {c->evr0, c->evr1, c->evt0, c->evt1})
+        if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return AQ_OK;
@@ -281,6 +285,10 @@ int aq_create(aq_ctx** out, int device, int n, int p, int q_local, const double*
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->evr0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->evr1);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->evt0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->evt1);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->ymat, 0, sizeof(double) * (size_t)c->q_pad * cfg.n_pad, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->gam, 0, sizeof(double) * pq, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->mu, 0, sizeof(double) * pq, c->stream);
@@ -396,6 +404,7 @@ int aq_refresh_tables(aq_ctx* c, const double* theta_vb, const double* zeta_vb, 
     AQ_CUDA(cudaMemcpyAsync(c->zeta, zeta_vb, sizeof(double) * c->q, cudaMemcpyHostToDevice, c->stream));
     const int c_is_one = std::fabs(c_next - 1.0) < 1.5e-8;  // isTRUE(all.equal(c, 1)), R/update_vb.R:219
     dim3 grid((c->q + 255) / 256, (c->p + kTabRowsPerBlock - 1) / kTabRowsPerBlock);
+    AQ_CUDA(cudaEventRecord(c->evt0, c->stream));
     tables_kernel<<<grid, 256, 0, c->stream>>>(c->theta, c->zeta, c->p, c->q, c->q_pad, c_is_one ? 1.0 : std::sqrt(c_next),
                                                c_is_one, c->gam, c->dtab, c->wtab, c->i0tab, elbo_b_part ? 1 : 0,
                                                c->partials);
@@ -407,7 +416,9 @@ int aq_refresh_tables(aq_ctx* c, const double* theta_vb, const double* zeta_vb, 
         c->launches++;
         AQ_CUDA(cudaMemcpyAsync(elbo_b_part, c->scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     }
+    AQ_CUDA(cudaEventRecord(c->evt1, c->stream));
     AQ_CUDA(cudaStreamSynchronize(c->stream));
+    AQ_CUDA(cudaEventElapsedTime(&c->last_tables_ms, c->evt0, c->evt1));
     c->have_tables = true;
     return AQ_OK;
 }
@@ -437,10 +448,13 @@ int aq_rowsums_zpart_dev(aq_ctx* c, double** rowsum_zpart_dev) {
     if (!c || !rowsum_zpart_dev) return fail(AQ_EINVAL, "NULL argument");
     if (!c->have_state || !c->have_tables) return fail(AQ_ESTATE, "aq_rowsums_zpart before state/tables");
     AQ_CUDA(cudaSetDevice(c->device));
+    AQ_CUDA(cudaEventRecord(c->evr0, c->stream));
     rowsums_kernel<<<(c->p + 7) / 8, 256, 0, c->stream>>>(c->gam, c->wtab, c->i0tab, c->p, c->q, c->q_pad, c->rowsum);
     AQ_CUDA(cudaGetLastError());
     c->launches++;
+    AQ_CUDA(cudaEventRecord(c->evr1, c->stream));
     AQ_CUDA(cudaStreamSynchronize(c->stream));
+    AQ_CUDA(cudaEventElapsedTime(&c->last_rows_ms, c->evr0, c->evr1));
     *rowsum_zpart_dev = c->rowsum;
     return AQ_OK;
 }
@@ -459,6 +473,15 @@ int64_t aq_launch_count(const aq_ctx* c) { return c ? c->launches : 0; }
 int aq_last_sweep_ms(const aq_ctx* c, float* ms) {
     if (!c || !ms) return fail(AQ_EINVAL, "NULL argument");
     *ms = c->last_ms;
+    return AQ_OK;
+}
+
+int aq_last_ms(const aq_ctx* c, int which, float* ms) {
+    if (!c || !ms) return fail(AQ_EINVAL, "NULL argument");
+    if (which == 0) *ms = c->last_ms;
+    else if (which == 1) *ms = c->last_rows_ms;
+    else if (which == 2) *ms = c->last_tables_ms;
+    else return fail(AQ_EINVAL, "aq_last_ms: which must be 0 (sweep), 1 (row sums) or 2 (tables)");
     return AQ_OK;
 }
 

@@ -109,5 +109,11 @@ class SweepContext:
         _lib.check(self._lib.aq_last_sweep_ms(self._ctx, ctypes.byref(ms)))
         return ms.value
 
+    def last_ms(self, which):
+        """Device time (ms) of the last sweep (0), row-sum (1) or table (2) kernel group."""
+        ms = ctypes.c_float()
+        _lib.check(self._lib.aq_last_ms(self._ctx, ctypes.c_int(which), ctypes.byref(ms)))
+        return ms.value
+
     def sync(self):
         _lib.check(self._lib.aq_sync(self._ctx))

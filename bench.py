@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Benchmark of the CAVI sweep hot path: SNP x trait updates/s (BASELINE.json's metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2] [--impl ours|reference]
+
+A "step" is one full VB iteration of the BASELINE config as `atlasqtl()` would run it: the host
+q-/p-sized algebra, the fused sweep kernel (coreDualLoop + its reductions), the row sums of Z, the
+all-reduce (N > 1) and the table refresh (+ ELBO part once annealing is over).
+
+  value  updates/s with everything resident in HBM: p*q*K / (device time of the K steps' kernels,
+         CUDA events on the library's stream, max over ranks)
+  e2e    the same K steps through the public host API / C ABI with HOST buffers (per-step H2D of the
+         per-trait vectors and theta/zeta, D2H of the column / row sums), wall clock between
+         barrier + device synchronize, max over ranks
+  N > 1  traits are sharded over ranks (strong scaling: the total q is fixed), one NCCL all-reduce per sweep.
+
+`--impl reference` times the reference's own coreDualLoop (oracle/_ref: src/coreLoop.cpp compiled
+unmodified) on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FP64_PEAK_TFLOPS = 37.05  # measured DMMA m8n8k4 peak on this pool's B200 (profiles/r1_fp64_peaks_microbench.txt);
+                          # MEASURED_PEAKS.json has no fp64 entry (bf16 / HBM only)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------- workload
+def make_workload(name, k_first, k_last, seed=123, threads=None):
+    """Synthetic data + default hyper / init of BASELINE config `name` for the trait slab [k_first, k_last)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from scipy import special as sp
+
+    from atlasqtl_b200 import hyper_init, synthetic
+    cfg = dict(synthetic.CONFIGS[name])
+    n, p, q = cfg["n"], cfg["p"], cfg["q"]
+    rng = np.random.default_rng(seed)
+    # genotypes, standardised (constant columns are re-drawn rather than dropped so that p stays as named)
+    X = np.empty((n, p), order="F")
+    maf = 0.25
+    for j0 in range(0, p, 8192):
+        j1 = min(p, j0 + 8192)
+        G = rng.binomial(2, maf, size=(n, j1 - j0)).astype(np.float64)
+        sd = G.std(axis=0, ddof=1)
+        bad = sd == 0
+        if bad.any():
+            G[: 2, bad] = [[0.0], [1.0]]
+            sd = G.std(axis=0, ddof=1)
+        X[:, j0:j1] = (G - G.mean(axis=0)) / sd
+    p_act = cfg.get("p_act", cfg.get("hotspots", 20))
+    q_act = cfg.get("q_act", q)
+    act = rng.choice(p, size=p_act, replace=False)
+    traits_act = rng.choice(q, size=q_act, replace=False)
+    beta = np.zeros((p_act, q))
+    pat = rng.random((p_act, q_act)) < 0.2
+    beta[:, traits_act] = pat * rng.normal(0.0, cfg.get("beta_sd", 1.0), size=(p_act, q_act))
+    ql = k_last - k_first
+    Y = X[:, act] @ beta[:, k_first:k_last] + np.random.default_rng(seed + 1 + k_first).normal(size=(n, ql))
+    Y = np.asfortranarray(Y - Y.mean(axis=0))
+    p0 = (max(1.0, float(pat.sum(axis=0).mean())), 10.0)
+    t02 = hyper_init._solve_t02(p, p0)
+    n0 = float(hyper_init.get_mu(p0[0], t02, p))
+    tau0 = 1.0  # ~ 1 / median var(Y_k) of the recipe (unit noise); fixed so that every rank uses the same value
+    hyper = hyper_init.set_hyper(q, p, tau0, 1.0, n0, 1e-2, 1.0, t02)
+    # auto_set_init_ distributions (R/set_hyper_init.R:388-405), drawn slab-wise in parallel
+    gam = np.empty((p, ql), order="F")
+    mu = np.empty((p, ql), order="F")
+    sd0 = 1e-4 + t02
+    chunk = 256
+
+    def fill(k0):
+        r = np.random.default_rng([seed, 7, k_first + k0])
+        k1 = min(ql, k0 + chunk)
+        z = r.standard_normal((k1 - k0, p), dtype=np.float32)
+        gam[:, k0:k1] = sp.ndtr(n0 + sd0 * z).T
+        mu[:, k0:k1] = r.standard_normal((k1 - k0, p), dtype=np.float32).T
+
+    with ThreadPoolExecutor(threads or min(32, os.cpu_count() or 1)) as ex:
+        list(ex.map(fill, range(0, ql, chunk)))
+    r = np.random.default_rng(seed + 3)
+    sig02_inv = float(r.gamma(shape=max(p, q), scale=1.0))
+    init = dict(q_init=q, p_init=p, gam_vb=gam, mu_beta_vb=mu, sig02_inv_vb=sig02_inv,
+                sig2_beta_vb=1 / r.gamma(shape=2.0, scale=1e-2 * tau0, size=q),
+                sig2_theta_vb=1 / (q + r.gamma(shape=sig02_inv * q, scale=1.0, size=p)),
+                tau_vb=np.full(q, tau0), theta_vb=r.normal(0.0, 1 / np.sqrt(sig02_inv * q), size=p),
+                zeta_vb=r.normal(n0, np.sqrt(t02), size=q))
+    return cfg, X, Y, hyper, init
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        rows = [r for r in self.rows if len(r) == 6 and r[0].isdigit()]
+        if not rows:
+            return None
+        sm = sorted(int(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(rows[0][1]), "reasons": reasons, "samples": len(rows)}
+
+
+# ----------------------------------------------------------------------------- CPU arms
+def reference_sample(cfg, X, Y, hyper, init, p_s=8192, traits_per_thread=1, threads=None, steps=2, warmup=1):
+    """Time the reference's own coreDualLoop on a bounded sample: the first p_s SNPs (its p x p Gram of the full
+    p does not fit / cannot be formed in minutes) x `threads * traits_per_thread` traits, one disjoint sample_q
+    range per host thread (traits are independent, so concurrent calls on disjoint columns are valid)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from scipy import special as sp
+
+    from oracle import native
+    threads = threads or (os.cpu_count() or 1)
+    n, p = X.shape
+    p_s = min(p, p_s)
+    q_s = min(Y.shape[1], threads * traits_per_thread)
+    Xs = np.asfortranarray(X[:, :p_s])
+    Ys = np.asfortranarray(Y[:, :q_s])
+    kind = "reference" if native.ref_available() else "port"
+    impl = "reference" if kind == "reference" else "oracle"
+    t0 = time.time()
+    cp_X = np.asfortranarray(Xs.T @ Xs)
+    cp_Y_X = np.asfortranarray(Ys.T @ Xs)
+    gam = np.asfortranarray(init["gam_vb"][:p_s, :q_s].copy())
+    mu = np.asfortranarray(init["mu_beta_vb"][:p_s, :q_s].copy())
+    beta = np.asfortranarray(gam * mu)
+    cbx = np.asfortranarray(cp_X @ beta)
+    setup_s = time.time() - t0
+    u = init["theta_vb"][:p_s, None] + init["zeta_vb"][None, :q_s]
+    lp, lq = np.asfortranarray(sp.log_ndtr(u)), np.asfortranarray(sp.log_ndtr(-u))
+    tau = np.ascontiguousarray(init["tau_vb"][:q_s])
+    sig2 = 1.0 / ((n - 1 + 1.0) * tau)
+    log_tau = np.log(tau)
+    order = np.arange(p_s, dtype=np.int32)
+    ranges = [np.arange(t * q_s // threads, (t + 1) * q_s // threads, dtype=np.int32) for t in range(threads)]
+    ranges = [r for r in ranges if len(r)]
+
+    def one(rng_q):
+        native.core_dual_loop(cp_X, cp_Y_X, gam, lp, lq, 0.0, log_tau, beta, cbx, mu, sig2, tau, order, rng_q,
+                              c=1.0, impl=impl)
+
+    times = []
+    with ThreadPoolExecutor(len(ranges)) as ex:
+        for s in range(warmup + steps):
+            t0 = time.time()
+            list(ex.map(one, ranges))
+            dt = time.time() - t0
+            if s >= warmup:
+                times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = p_s * q_s / (ms / 1e3)
+    return dict(value=value, unit="SNPxtrait updates/s", cores=len(ranges), kind=kind, ms_per_step=ms,
+                sample=f"coreDualLoop (dual/Gram form, as the reference runs it), n={n}, first {p_s} of {p} SNPs x "
+                       f"{q_s} traits, {len(ranges)} host threads on disjoint sample_q ranges; Gram set-up {setup_s:.1f} s "
+                       f"not timed; dual-form cost per update grows with p, so at the full p this is ~{p_s / p:.3g}x",
+                value_at_full_p_est=value * p_s / p)
+
+
+def port_sample(X, Y, init, threads=None, target_s=6.0):
+    """Best-effort CPU (ours, primal form, all host threads) on a q-slice of the full-n, full-p workload."""
+    from scipy import special as sp
+
+    from oracle import native
+    threads = threads or (os.cpu_count() or 1)
+    n, p = X.shape
+    q_s = min(Y.shape[1], max(threads, int(target_s * threads * 1.5e9 / (4.0 * n * p))))
+    Ys = np.asfortranarray(Y[:, :q_s])
+    gam = np.asfortranarray(init["gam_vb"][:, :q_s].copy())
+    mu = np.asfortranarray(init["mu_beta_vb"][:, :q_s].copy())
+    beta = np.asfortranarray(gam * mu)
+    R = native.residual(X, Ys, beta)
+    xn = np.asfortranarray(np.sum(X ** 2, axis=0))
+    u = init["theta_vb"][:, None] + init["zeta_vb"][None, :q_s]
+    lp, lq = np.asfortranarray(sp.log_ndtr(u)), np.asfortranarray(sp.log_ndtr(-u))
+    tau = np.ascontiguousarray(init["tau_vb"][:q_s])
+    sig2 = 1.0 / ((n - 1 + 1.0) * tau)
+    t0 = time.time()
+    native.sweep_primal(X, xn, R, gam, lp, lq, 0.0, np.log(tau), beta, mu, sig2, tau, np.arange(p, dtype=np.int32),
+                        c=1.0, nthreads=threads)
+    dt = time.time() - t0
+    return dict(value=p * q_s / dt, unit="SNPxtrait updates/s", cores=threads, kind="port",
+                sample=f"oracle primal sweep, n={n}, p={p}, {q_s} traits, {threads} threads, {dt:.1f} s")
+
+
+# ----------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="C2")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    W, K = max(args.warmup, 0), max(args.steps, 1)
+
+    from atlasqtl_b200 import synthetic
+    from atlasqtl_b200.dist import slab_bounds
+    cfg0 = synthetic.CONFIGS[args.config]
+    n, p, q = cfg0["n"], cfg0["p"], cfg0["q"]
+    anneal = cfg0.get("anneal")
+    config = {"workload": f"{args.config}: synthetic n={n}, p={p} SNPs, q={q} traits, anneal={anneal}, fp64; "
+                          f"first {W}+{K} VB iterations", "n": n, "p": p, "q": q,
+              "l2": "inputs larger than L2 (p x q arrays stream from HBM every step)",
+              "parallelism": f"traits sharded over {world} GPU(s), X replicated"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import native
+        native.build()
+        ws = make_workload(args.config, 0, min(q, 4 * (os.cpu_count() or 1)))
+        res = reference_sample(*ws, steps=K, warmup=W)
+        line = {"impl": "reference", "metric": "SNPxtrait CAVI updates/s", "value": res["value"],
+                "unit": "updates/s", "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": res["ms_per_step"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config, "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "value_at_full_p_est": res["value_at_full_p_est"],
+                "e2e": {"value": res["value"], "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch
+    from atlasqtl_b200 import core
+    from atlasqtl_b200.device import SweepContext
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the hot path")
+    torch.cuda.set_device(local_rank)
+    comm = None
+    if world > 1:
+        import torch.distributed as dist
+        from atlasqtl_b200.dist import TorchComm
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        comm = TorchComm()
+    k0, k1 = slab_bounds(q, rank, world)
+    t_setup = time.time()
+    cfg, X, Y, hyper, init = make_workload(args.config, k0, k1)
+    log(f"[rank {rank}] workload built in {time.time() - t_setup:.1f} s (slab {k0}:{k1})")
+
+    def barrier_sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+    marks, launches = {}, {}
+    sampler = ClockSampler(local_rank)
+
+    def hook(it, ctx):
+        if it == W + 1:
+            ctx.sync()
+            barrier_sync()
+            if rank == 0:
+                sampler.start()
+            launches["t0"] = ctx.launch_count()
+            marks["t0"] = time.perf_counter()
+        if it == W + K + 1:
+            ctx.sync()
+            barrier_sync()
+            marks["t1"] = time.perf_counter()
+            launches["t1"] = ctx.launch_count()
+
+    trace = []
+    t_up = time.time()
+    ctx = SweepContext(X, Y, device=local_rank)
+    log(f"[rank {rank}] context created in {time.time() - t_up:.1f} s")
+    try:
+        core.atlasqtl_global_local_core_(Y, X, q, anneal, 1, 1e-300, W + K, 0, hyper, init, debug=False, comm=comm,
+                                         slab=(k0, k1), ctx=ctx, trace=trace, iter_hook=hook)
+        clocks = sampler.stop() if rank == 0 else None
+        timed = [r for r in trace if W < r["it"] <= W + K]
+        dev_ms = sum(r["sweep_ms"] + r["rows_ms"] + r["tables_ms"] for r in timed)
+        sweep_ms = float(np.mean([r["sweep_ms"] for r in timed]))
+        wall_ms = 1e3 * (marks["t1"] - marks["t0"])
+        red = np.array([dev_ms, wall_ms, sweep_ms])
+        if world > 1:
+            t = torch.tensor(red, device="cuda")
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            red = t.cpu().numpy()
+        dev_ms, wall_ms, sweep_ms_max = (float(v) for v in red)
+        ql = k1 - k0
+        dims = ctx.dims()
+        h2d = 8 * (3 * ql + p + ql) + (8 * (p + 2) if world > 1 else 0)
+        d2h = 8 * (5 * dims["q_pad"] + p + 1) + (8 * (p + 2) if world > 1 else 0)
+        n_launch = launches["t1"] - launches["t0"]
+    finally:
+        ctx.close()
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+    flops_per_sweep = 4.0 * n * p * ql  # algorithmic: 2n (X_j'r) + 2n (rank-1 update) per SNP x trait, this rank
+    achieved = flops_per_sweep / (sweep_ms * 1e-3) / 1e12
+    line = {"metric": "SNPxtrait CAVI updates/s", "value": p * q * K / (dev_ms * 1e-3), "unit": "updates/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "e2e": {"value": p * q * K / (wall_ms * 1e-3), "unit": "updates/s", "ms_per_step": wall_ms / K,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(n_launch),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                         "frac": achieved / FP64_PEAK_TFLOPS, "traffic": None,
+                         "kernel": "sweep_kernel (fp64 DMMA m8n8k4)", "ms": sweep_ms,
+                         "peak_source": "measured fp64 DMMA peak, tools/microbench/fp64_peaks.cu on this pool "
+                                        "(MEASURED_PEAKS.json has no fp64 entry)",
+                         "algorithmic": "4*n flops per SNPxtrait update"},
+            "clocks": clocks,
+            "per_step_ms": {"sweep": sweep_ms, "rowsums": float(np.mean([r["rows_ms"] for r in timed])),
+                            "tables": float(np.mean([r["tables_ms"] for r in timed]))}}
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import native
+            native.build()
+            ref = reference_sample(cfg, X, Y, hyper, init, steps=2, warmup=1)
+            line["cpu_baseline"] = {k: ref[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"]["value_at_full_p_est"] = ref["value_at_full_p_est"]
+            line["cpu_port"] = port_sample(X, Y, init)
+        except Exception as e:  # the baseline is a report, never the product path
+            line["cpu_baseline"] = {"error": repr(e)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

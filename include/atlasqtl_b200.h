@@ -131,6 +131,8 @@ int64_t aq_launch_count(const aq_ctx* ctx);
 
 /* Device time of the last aq_sweep's main kernel in milliseconds (CUDA events on the context's stream). */
 int aq_last_sweep_ms(const aq_ctx* ctx, float* ms);
+/* Same for the last launch of kernel group `which`: 0 sweep, 1 row sums (aq_rowsums_zpart), 2 tables (+ ELBO part). */
+int aq_last_ms(const aq_ctx* ctx, int which, float* ms);
 
 /* Block until everything queued on the context's stream has finished. */
 int aq_sync(aq_ctx* ctx);
