@@ -33,13 +33,14 @@ int fail(int code, const std::string& msg) {
         }                                                                                               \
     } while (0)
 
-// ---- kernel configurations (SweepCfg<WS, WT, MT, NT>): picked by n at aq_create time
-using CfgA16 = SweepCfg<8, 1, 2, 16>;  // n <= 1024, 16 traits / tile
-using CfgA8 = SweepCfg<8, 1, 2, 8>;    // n <= 512 ... only used when it wastes less padding
-using CfgB16 = SweepCfg<4, 2, 2, 16>;  // n <= 512, 32 traits / tile
-using CfgB8 = SweepCfg<4, 2, 2, 8>;    // n <= 256
-using CfgC16 = SweepCfg<2, 4, 2, 16>;  // n <= 256, 64 traits / tile
-using CfgC8 = SweepCfg<2, 4, 2, 8>;    // n <= 128
+// ---- kernel configurations (SweepCfg<WS, WT, MT, NT>): picked by n at aq_create time.
+// 9 MMA warps split the samples (n_pad = 72 NT); each holds MT 8-trait tiles: MT * NT * 2 accumulator doubles.
+using CfgN1008 = SweepCfg<9, 1, 2, 14>;  // n <= 1008, 16 traits / tile
+using CfgN720 = SweepCfg<9, 1, 3, 10>;   // n <= 720,  24 traits / tile
+using CfgN504 = SweepCfg<9, 1, 4, 7>;    // n <= 504,  32 traits / tile
+using CfgN360 = SweepCfg<9, 1, 6, 5>;    // n <= 360,  48 traits / tile
+using CfgN216 = SweepCfg<9, 1, 8, 3>;    // n <= 216,  64 traits / tile
+using CfgN144 = SweepCfg<9, 1, 8, 2>;    // n <= 144,  64 traits / tile
 
 struct CfgInfo {
     int id, n_pad, xs, kT, threads;
@@ -51,10 +52,12 @@ CfgInfo info(int id) {
 }
 
 bool pick_cfg(int n, CfgInfo* out) {
-    if (n <= 128) *out = info<CfgC8>(5);
-    else if (n <= 256) *out = info<CfgC16>(4);
-    else if (n <= 512) *out = info<CfgB16>(2);
-    else if (n <= 1024) *out = info<CfgA16>(0);
+    if (n <= 144) *out = info<CfgN144>(5);
+    else if (n <= 216) *out = info<CfgN216>(4);
+    else if (n <= 360) *out = info<CfgN360>(3);
+    else if (n <= 504) *out = info<CfgN504>(2);
+    else if (n <= 720) *out = info<CfgN720>(1);
+    else if (n <= 1008) *out = info<CfgN1008>(0);
     else return false;
     return true;
 }
@@ -130,10 +133,12 @@ int launch_sweep(aq_ctx* c, int mode, double cc, double log_sig2_inv) {
     P.cs_z = c->ovec + 4 * (size_t)c->q_pad;
     P.mode = mode;
     switch (c->cfg.id) {
-        case 0: return launch_sweep_t<CfgA16>(c, P);
-        case 2: return launch_sweep_t<CfgB16>(c, P);
-        case 4: return launch_sweep_t<CfgC16>(c, P);
-        case 5: return launch_sweep_t<CfgC8>(c, P);
+        case 0: return launch_sweep_t<CfgN1008>(c, P);
+        case 1: return launch_sweep_t<CfgN720>(c, P);
+        case 2: return launch_sweep_t<CfgN504>(c, P);
+        case 3: return launch_sweep_t<CfgN360>(c, P);
+        case 4: return launch_sweep_t<CfgN216>(c, P);
+        case 5: return launch_sweep_t<CfgN144>(c, P);
     }
     return fail(AQ_EUNSUPPORTED, "no kernel configuration");
 }
@@ -236,7 +241,7 @@ int aq_create(aq_ctx** out, int device, int n, int p, int q_local, const double*
     if (n < 2 || p < 1 || q_local < 1) return fail(AQ_EINVAL, "aq_create: need n >= 2, p >= 1, q >= 1");
     CfgInfo cfg;
     if (!pick_cfg(n, &cfg))
-        return fail(AQ_EUNSUPPORTED, "aq_create: n > 1024 needs the sample-split (cluster) kernel, not in this build");
+        return fail(AQ_EUNSUPPORTED, "aq_create: n > 1008 needs the sample-split (cluster) kernel, not in this build");
     int sm = 0;
     int rc = aq_device_info(device, &sm, nullptr, nullptr);
     if (rc != AQ_OK) return rc;

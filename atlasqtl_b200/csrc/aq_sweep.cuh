@@ -1,8 +1,12 @@
 // The CAVI Gauss-Seidel sweep kernel (sm_100a): coreDualLoop (reference src/coreLoop.cpp:38-86) in
 // sample space, blocked over SNPs, one persistent CTA per trait tile.
 //
-// Roles inside a CTA (warp-specialised, no __syncthreads in the steady state):
-//   8 "MMA" warps   hold the tile's residual R^T (traits x samples) in REGISTERS as the accumulator
+// Roles inside a CTA (warp-specialised, no __syncthreads in the steady state).  The fp64 tensor op
+// (DMMA) and scalar fp64 math share one pipe per SM sub-partition (SMSP = warp id % 4); a chain lane's
+// dependent DFMA/DADD sequence queued behind 16-cycle DMMAs runs ~2-3x slower (ncu: stall_math on the
+// chain warp, profiles/r1_ncu_sweep_c4_v1.txt).  So the 9 MMA warps live on SMSPs 0-2 (warp id % 4 != 3)
+// and the serial chain gets SMSP 3 to itself (warp ids 3, 7, 11):
+//   9 "MMA" warps   hold the tile's residual R^T (traits x samples) in REGISTERS as the accumulator
 //                   fragments of the rank-8 update  R^T -= Delta^T X_b^T  (DMMA m8n8k4), and reuse the very
 //                   same registers as the A operand of  S^T = R^T X_b  -- the accumulator layout
 //                   C[m][2l+e] is an A fragment A[m][l] once the contraction index is read as 2l+e, so the
@@ -58,7 +62,7 @@ struct SweepCfg {
     static constexpr int kChainWarps = (kT + 31) / 32;
     static constexpr int kNPad = WS * NT * 8;        // samples, padded
     static constexpr int kXS = kNPad + ((kNPad % 16 == 0) ? 8 : 0);  // tile row stride == 8 (mod 16) doubles
-    static constexpr int kThreads = (kMmaWarps + kChainWarps + 1) * 32;
+    static constexpr int kThreads = 12 * 32;  // warps 3, 7, 11 (SMSP 3): chain warp(s) + producer
     static constexpr int kStages = 3;
     static constexpr size_t kTileDoubles = (size_t)kBlk * kXS + kTileTail;
     static constexpr size_t kSpartDoubles = (size_t)2 * WS * kBlk * kT;
@@ -66,7 +70,8 @@ struct SweepCfg {
     static constexpr size_t kRsqDoubles = (size_t)WS * kT;
     static constexpr size_t kSmemBytes =
         (kStages * kTileDoubles + kSpartDoubles + kDbufDoubles + kRsqDoubles) * sizeof(double) + 16 * sizeof(uint64_t);
-    static_assert(kMmaWarps == 8, "8 MMA warps");
+    static_assert(kMmaWarps == 9, "9 MMA warps: three per SMSP on SMSPs 0-2");
+    static_assert(kChainWarps <= 2, "at most 64 traits per tile");
     static_assert(kXS % 16 == 8, "row stride must be 8 mod 16 doubles");
 };
 
@@ -85,7 +90,11 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
     uint64_t* sdone = bars + 2 * kStages;      // [2]  8 MMA warps wrote their S partials
     uint64_t* dready = bars + 2 * kStages + 2; // [2]  chain warps published -Delta
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // role map: SMSP 3 (wid % 4 == 3) hosts the special warps, SMSPs 0-2 the MMA warps
+    const bool is_special = (wid & 3) == 3;
+    const int mma_idx = wid - (wid >> 2);   // 0..8 for MMA warps
+    const int special_idx = wid >> 2;       // 0..2 for special warps
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], Cfg::kMmaWarps); }
         for (int s = 0; s < 2; ++s) { mbar_init(&sdone[s], Cfg::kMmaWarps); mbar_init(&dready[s], Cfg::kChainWarps); }
@@ -97,7 +106,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
     const int my_tiles = (P.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const uint32_t tile_bytes = (uint32_t)(Cfg::kTileDoubles * sizeof(double));
 
-    if (warp == Cfg::kMmaWarps + Cfg::kChainWarps) {
+    if (is_special && special_idx == Cfg::kChainWarps) {
         // ------------------------------------------------------------------ producer
         if (lane == 0) {
             const long total = (long)my_tiles * nb;
@@ -110,9 +119,10 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 bulk_g2s(tiles + stage * Cfg::kTileDoubles, P.xtiles + (size_t)b * P.tile_stride, tile_bytes, &full[stage]);
             }
         }
-    } else if (warp < Cfg::kMmaWarps) {
+    } else if (!is_special) {
         // ------------------------------------------------------------------ MMA warps
-        const int ws = warp % WS, wt = warp / WS;
+        const int ws = mma_idx % WS, wt = mma_idx / WS;
+        const int mtid = mma_idx * 32 + lane;
         const int g = lane >> 2, l = lane & 3;
         const int i0 = ws * NT * 8;
         const int tr0 = wt * MT * 8;
@@ -175,6 +185,12 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     nd[mt][0] = db[(tr0 + mt * 8 + g) * kBlk + l];
                     nd[mt][1] = db[(tr0 + mt * 8 + g) * kBlk + l + 4];
                 }
+                if (P.mode != 0) {
+                    // no S phase paces the chain in this mode: tell it that -Delta buffer (gb & 1) has been consumed,
+                    // otherwise it could run two blocks ahead, overwrite the buffer and alias the barrier phase
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sdone[gb & 1]);
+                }
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     const double x0 = xt[offU0 + nt * 8];
@@ -206,17 +222,17 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 if (l == 0) rsqs[ws * kT + tr0 + mt * 8 + g] = ss;
             }
             asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kMmaWarps * 32) : "memory");
-            if (threadIdx.x < kT) {
+            if (mtid < kT) {
                 double ss = 0.0;
 #pragma unroll
-                for (int w2 = 0; w2 < WS; ++w2) ss += rsqs[w2 * kT + threadIdx.x];
-                if (k0 + (int)threadIdx.x < P.q) P.rsq[k0 + threadIdx.x] = ss;
+                for (int w2 = 0; w2 < WS; ++w2) ss += rsqs[w2 * kT + mtid];
+                if (k0 + mtid < P.q) P.rsq[k0 + mtid] = ss;
             }
             asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kMmaWarps * 32) : "memory");
         }
-    } else {
+    } else if (special_idx < Cfg::kChainWarps) {
         // ------------------------------------------------------------------ chain warps (one lane per trait)
-        const int cw = warp - Cfg::kMmaWarps;
+        const int cw = special_idx;
         const int tl = cw * 32 + lane;
         const bool active = tl < kT;
         const int tls = active ? tl : 0;  // inactive lanes shadow trait 0 without side effects
@@ -302,6 +318,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                         }
                     }
                 } else {
+                    if (gb >= 2) mbar_wait(&sdone[gb & 1], (uint32_t)(((gb >> 1) - 1) & 1));  // buffer free again
 #pragma unroll
                     for (int t = 0; t < kBlk; ++t) {
                         const bool live = id[t] >= 0;

@@ -71,7 +71,8 @@ def make_workload(name, k_first, k_last, seed=123, threads=None):
     ql = k_last - k_first
     Y = X[:, act] @ beta[:, k_first:k_last] + np.random.default_rng(seed + 1 + k_first).normal(size=(n, ql))
     Y = np.asfortranarray(Y - Y.mean(axis=0))
-    p0 = (max(1.0, float(pat.sum(axis=0).mean())), 10.0)
+    e_p = max(1.0, float(pat.sum(axis=0).mean()))
+    p0 = (e_p, max(10.0, 2.0 * e_p))  # (mean, variance) of the prior number of active SNPs per trait
     t02 = hyper_init._solve_t02(p, p0)
     n0 = float(hyper_init.get_mu(p0[0], t02, p))
     tau0 = 1.0  # ~ 1 / median var(Y_k) of the recipe (unit noise); fixed so that every rank uses the same value
