@@ -65,7 +65,8 @@ struct SweepCfg {
     static constexpr int kThreads = 12 * 32;  // warps 3, 7, 11 (SMSP 3): chain warp(s) + producer
     static constexpr int kStages = 3;
     static constexpr size_t kTileDoubles = (size_t)kBlk * kXS + kTileTail;
-    static constexpr size_t kSpartDoubles = (size_t)2 * WS * kBlk * kT;
+    static constexpr int kSps = 10;  // S-partial row stride (doubles): 8 SNP slots + 2 pad => conflict-free 16-byte accesses
+    static constexpr size_t kSpartDoubles = (size_t)2 * WS * kT * kSps;
     static constexpr size_t kDbufDoubles = (size_t)2 * kT * kBlk;
     static constexpr size_t kRsqDoubles = (size_t)WS * kT;
     static constexpr size_t kSmemBytes =
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
     constexpr int kStages = Cfg::kStages;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* tiles = reinterpret_cast<double*>(smem_raw);
-    double* spart = tiles + kStages * Cfg::kTileDoubles;  // [2][WS][kBlk][kT]
+    double* spart = tiles + kStages * Cfg::kTileDoubles;  // [2][WS][kT][kSps]
     double* dbuf = spart + Cfg::kSpartDoubles;            // [2][kT][kBlk]  (holds -Delta)
     double* rsqs = dbuf + Cfg::kDbufDoubles;              // [WS][kT]
     uint64_t* bars = reinterpret_cast<uint64_t*>(rsqs + Cfg::kRsqDoubles);
@@ -160,12 +161,13 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                         dmma(sa[mt][1][0], sa[mt][1][1], acc[mt][nt][1], xb.y);
                     }
                 }
-                double* sp = spart + ((size_t)(gbi & 1) * WS + ws) * kBlk * kT;
+                double* sp = spart + ((size_t)(gbi & 1) * WS + ws) * kT * Cfg::kSps;
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
-                    const int tl = tr0 + mt * 8 + g;
-                    sp[(2 * l) * kT + tl] = sa[mt][0][0] + sa[mt][1][0];
-                    sp[(2 * l + 1) * kT + tl] = sa[mt][0][1] + sa[mt][1][1];
+                    double2 v;  // C fragment: S^T[trait g + 8 mt][snp 2l, 2l + 1]
+                    v.x = sa[mt][0][0] + sa[mt][1][0];
+                    v.y = sa[mt][0][1] + sa[mt][1][1];
+                    *reinterpret_cast<double2*>(sp + (tr0 + mt * 8 + g) * Cfg::kSps + 2 * l) = v;
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sdone[gbi & 1]);
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 if (P.mode == 0 && b + 1 < nb) s_phase(gb + 1);
                 // ---- rank-8 update with -Delta_b
                 const int stage = (int)(gb % kStages);
-                mbar_wait(&full[stage], (uint32_t)((gb / kStages) & 1));
+                if (P.mode != 0) mbar_wait(&full[stage], (uint32_t)((gb / kStages) & 1));  // sweep mode: S phase waited
                 mbar_wait(&dready[gb & 1], (uint32_t)((gb >> 1) & 1));
                 const double* xt = tiles + stage * Cfg::kTileDoubles;
                 const double* db = dbuf + (size_t)(gb & 1) * kT * kBlk;
@@ -274,13 +276,17 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 double s[kBlk], dl[kBlk];
                 if (P.mode == 0) {
                     mbar_wait(&sdone[gb & 1], (uint32_t)((gb >> 1) & 1));
-                    const double* sp = spart + (size_t)(gb & 1) * WS * kBlk * kT;
+                    const double* sp = spart + (size_t)(gb & 1) * WS * kT * Cfg::kSps + tls * Cfg::kSps;
 #pragma unroll
-                    for (int t = 0; t < kBlk; ++t) {
-                        double v = 0.0;
+                    for (int t = 0; t < kBlk; ++t) s[t] = 0.0;
 #pragma unroll
-                        for (int w2 = 0; w2 < WS; ++w2) v += sp[(w2 * kBlk + t) * kT + tls];
-                        s[t] = v;
+                    for (int w2 = 0; w2 < WS; ++w2) {
+#pragma unroll
+                        for (int t = 0; t < kBlk; t += 2) {
+                            const double2 v = *reinterpret_cast<const double2*>(sp + w2 * kT * Cfg::kSps + t);
+                            s[t] += v.x;
+                            s[t + 1] += v.y;
+                        }
                     }
                     // look-ahead correction: S was formed before the previous block's update was applied
                     if (b > 0) {
