@@ -1,0 +1,178 @@
+"""GPU: golden vectors of the reference through the CUDA path, ragged / degenerate shapes, every kernel
+configuration, error behaviour of the C ABI, and size-independent properties at a BASELINE-scale shape."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from problems import make_problem, sweep_inputs
+
+pytestmark = pytest.mark.gpu
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "coredualloop_*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[14:-4] for p in GOLDEN])
+def test_cuda_sweep_matches_reference_golden(path):
+    """Outputs of the reference's own coreDualLoop (tests/golden/make_golden.py) vs the CUDA sweep."""
+    from atlasqtl_b200.device import SweepContext
+    d = dict(np.load(path))
+    X, Y = np.asfortranarray(d["X"]), np.asfortranarray(d["Y"])
+    with SweepContext(X, Y) as ctx:
+        ctx.set_order(d["order"])
+        ctx.set_state(d["gam"], d["mu"])
+        ctx.refresh_tables(d["theta"], d["zeta"], c_next=float(d["c"]))
+        ctx.sweep(float(d["c"]), float(d["log_sig2_inv"]), d["tau"], d["log_tau"], d["sig2_beta"])
+        st = ctx.get_state()
+        R = ctx.get_residual()
+    assert np.abs(st["gam_vb"] - d["out_gam"]).max() <= 1e-9      # north_star bound is 1e-8
+    assert np.abs(st["mu_beta_vb"] - d["out_mu"]).max() <= 1e-9
+    assert np.abs(st["beta_vb"] - d["out_beta"]).max() <= 1e-9
+    np.testing.assert_allclose(X.T @ (Y - R), d["out_cp_betaX_X"], atol=1e-8)  # the reference's running X'X beta
+
+
+def _cpu_sweep(native, X, Y, si, order):
+    gam, mu = si["gam"].copy(order="F"), si["mu"].copy(order="F")
+    beta = np.asfortranarray(gam * mu)
+    R = native.residual(X, Y, beta)
+    native.sweep_primal(X, np.asfortranarray((X ** 2).sum(0)), R, gam, si["log_Phi"], si["log_1_min_Phi"],
+                        si["log_sig2_inv"], si["log_tau"], beta, mu, si["sig2_beta"], si["tau"], order, c=si["c"],
+                        nthreads=4)
+    return gam, mu, R
+
+
+@pytest.mark.parametrize("n,p,q", [
+    (30, 1, 1),        # a single pair
+    (30, 7, 3),        # p < one SNP block
+    (64, 9, 65),       # p, q just past a block / tile boundary
+    (144, 17, 33), (150, 40, 70), (216, 24, 64), (250, 33, 50), (360, 16, 48), (400, 20, 33),
+    (504, 25, 32), (600, 30, 25), (720, 12, 24), (800, 21, 17), (1008, 10, 16),   # every kernel configuration
+])
+def test_ragged_shapes_and_all_configs(oracle_built, n, p, q):
+    from atlasqtl_b200.device import SweepContext
+    native = oracle_built
+    rng = np.random.default_rng(n + p + q)
+    X = rng.normal(size=(n, p))
+    X = np.asfortranarray((X - X.mean(0)) / X.std(0, ddof=1))
+    Y = rng.normal(size=(n, q))
+    Y = np.asfortranarray(Y - Y.mean(0))
+    si = sweep_inputs(X, Y, None, c=0.9)
+    order = rng.permutation(p).astype(np.int32)
+    g_ref, m_ref, R_ref = _cpu_sweep(native, X, Y, si, order)
+    with SweepContext(X, Y) as ctx:
+        ctx.set_order(order)
+        ctx.set_state(si["gam"], si["mu"])
+        ctx.refresh_tables(si["theta"], si["zeta"], c_next=0.9)
+        out = ctx.sweep(0.9, si["log_sig2_inv"], si["tau"], si["log_tau"], si["sig2_beta"])
+        st = ctx.get_state()
+        R = ctx.get_residual()
+    assert np.abs(st["gam_vb"] - g_ref).max() <= 1e-9
+    assert np.abs(st["mu_beta_vb"] - m_ref).max() <= 1e-9
+    np.testing.assert_allclose(R, R_ref, atol=1e-9)
+    np.testing.assert_allclose(out["resid_sq"], (R_ref ** 2).sum(0), rtol=1e-10)
+
+
+def test_two_sweeps_and_order_change(oracle_built):
+    """State stays on the device between calls; changing shuffled_ind re-tiles X and changes the result."""
+    from atlasqtl_b200.device import SweepContext
+    native = oracle_built
+    X, Y, hyper, init = make_problem(200, 120, 40)
+    p = X.shape[1]
+    si = sweep_inputs(X, Y, init, c=1.0)
+    o1 = np.arange(p, dtype=np.int32)
+    o2 = np.random.default_rng(3).permutation(p).astype(np.int32)
+    gam, mu = si["gam"].copy(order="F"), si["mu"].copy(order="F")
+    beta = np.asfortranarray(gam * mu)
+    R = native.residual(X, Y, beta)
+    xn = np.asfortranarray((X ** 2).sum(0))
+    for o in (o1, o2):
+        native.sweep_primal(X, xn, R, gam, si["log_Phi"], si["log_1_min_Phi"], si["log_sig2_inv"], si["log_tau"], beta, mu,
+                            si["sig2_beta"], si["tau"], o, c=1.0)
+    with SweepContext(X, Y) as ctx:
+        ctx.set_state(si["gam"], si["mu"])
+        ctx.refresh_tables(si["theta"], si["zeta"])
+        for o in (None, o2):
+            ctx.set_order(o)
+            ctx.sweep(1.0, si["log_sig2_inv"], si["tau"], si["log_tau"], si["sig2_beta"])
+        st = ctx.get_state()
+    assert np.abs(st["gam_vb"] - gam).max() <= 1e-9
+
+
+def test_error_behaviour():
+    from atlasqtl_b200 import _lib
+    from atlasqtl_b200.device import SweepContext
+    rng = np.random.default_rng(0)
+    X = np.asfortranarray(rng.normal(size=(40, 10)))
+    Y = np.asfortranarray(rng.normal(size=(40, 5)))
+    with SweepContext(X, Y) as ctx:
+        with pytest.raises(_lib.AtlasqtlB200Error, match="before aq_set_state"):
+            ctx.sweep(1.0, 0.0, np.ones(5), np.zeros(5), np.ones(5))
+        ctx.set_state(np.full((10, 5), 0.1), np.zeros((10, 5)))
+        with pytest.raises(_lib.AtlasqtlB200Error, match="before aq_refresh_tables"):
+            ctx.sweep(1.0, 0.0, np.ones(5), np.zeros(5), np.ones(5))
+        with pytest.raises(_lib.AtlasqtlB200Error, match="not a permutation"):
+            ctx.set_order(np.array([0, 1, 2, 3, 4, 5, 6, 7, 8, 8], dtype=np.int32))
+        with pytest.raises(_lib.AtlasqtlB200Error, match="not a permutation"):
+            ctx.set_order(np.array([0, 1, 2, 3, 4, 5, 6, 7, 8, 10], dtype=np.int32))
+        with pytest.raises(ValueError):
+            ctx.set_state(np.zeros((9, 5)), np.zeros((10, 5)))
+        ctx.refresh_tables(np.zeros(10), np.zeros(5))
+        with pytest.raises(_lib.AtlasqtlB200Error, match="c must be positive"):
+            ctx.sweep(0.0, 0.0, np.ones(5), np.zeros(5), np.ones(5))
+        ctx.sweep(1.0, 0.0, np.ones(5), np.zeros(5), np.ones(5))  # the context is still usable after errors
+
+
+def test_table_pass_matches_scipy_incl_tails():
+    """D, W, I0 and the ELBO-B part against SciPy's log_ndtr (R's pnorm(log.p=TRUE)), deep tails included."""
+    from scipy import special as sp
+
+    from atlasqtl_b200.device import SweepContext
+    rng = np.random.default_rng(4)
+    p, q, n = 64, 40, 30
+    X = np.asfortranarray(rng.normal(size=(n, p)))
+    Y = np.asfortranarray(rng.normal(size=(n, q)))
+    theta = np.linspace(-28, 9, p)
+    zeta = rng.normal(-1.0, 2.0, q)
+    gam = np.asfortranarray(rng.uniform(size=(p, q)) ** 6)
+    gam[0, 0], gam[1, 1] = 0.0, 1.0
+    u = theta[:, None] + zeta[None, :]
+    eps = np.finfo(float).eps ** 0.75
+    for c in (1.0, 0.5):
+        with SweepContext(X, Y) as ctx:
+            ctx.set_state(gam, np.zeros((p, q)))
+            part = ctx.refresh_tables(theta, zeta, c_next=c, want_elbo=True)
+            # the Z part is observable through the row sums: sum_k gam W + I0
+            rows = ctx.rowsums_zpart()
+        lp, lq = sp.log_ndtr(u), sp.log_ndtr(-u)
+        expect = np.sum(gam * lp + (1 - gam) * lq - gam * np.log(gam + eps) - (1 - gam) * np.log(1 - gam + eps))
+        assert abs(part - expect) <= 1e-12 * abs(expect)
+        U = np.sqrt(c) * u
+        lpU, lqU = sp.log_ndtr(U), sp.log_ndtr(-U)
+        m1 = np.maximum(np.exp(-U ** 2 / 2 - 0.5 * np.log(2 * np.pi) - lpU), -U)
+        m0 = np.minimum(-np.exp(-U ** 2 / 2 - 0.5 * np.log(2 * np.pi) - lqU), -U)
+        np.testing.assert_allclose(rows, (gam * (m1 - m0) + m0).sum(axis=1), rtol=1e-11, atol=1e-10)
+
+
+def test_size_independent_properties_at_scale():
+    """BASELINE config C4 dimensions (n=500, p=10000, q=5000): no CPU oracle at this size, so check properties:
+    (1) the residual the sweep carried equals Y - X beta rebuilt from scratch from the downloaded state;
+    (2) a sweep at the fixed point of another sweep changes nothing it should not (column sums are consistent);
+    (3) gam_vb stays in [0, 1] and finite."""
+    import bench
+    from atlasqtl_b200.device import SweepContext
+    cfg, X, Y, hyper, init = bench.make_workload("C4", 0, 5000)
+    n, p = X.shape
+    q = Y.shape[1]
+    tau = np.full(q, 1.0)
+    sig2 = 1 / ((n - 1 + 1.0) * tau)
+    with SweepContext(X, Y) as ctx:
+        ctx.set_state(init["gam_vb"], init["mu_beta_vb"])
+        ctx.refresh_tables(init["theta_vb"], init["zeta_vb"])
+        out = ctx.sweep(1.0, 0.0, tau, np.zeros(q), sig2)
+        st = ctx.get_state()
+        again = ctx.set_state(st["gam_vb"], st["mu_beta_vb"])  # rebuilds Y - X beta from scratch (mode 1)
+    assert np.isfinite(st["gam_vb"]).all() and st["gam_vb"].min() >= 0 and st["gam_vb"].max() <= 1
+    np.testing.assert_allclose(out["resid_sq"], again["resid_sq"], rtol=1e-9)
+    np.testing.assert_allclose(out["colsum_gam"], st["gam_vb"].sum(axis=0), rtol=1e-11)
+    np.testing.assert_allclose(out["colsum_beta2"], (st["beta_vb"] ** 2).sum(axis=0), rtol=1e-10, atol=1e-300)
+    np.testing.assert_allclose(out["colsum_gam"], again["colsum_gam"], rtol=1e-12)

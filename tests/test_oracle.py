@@ -1,0 +1,118 @@
+"""CPU: pin the oracle.  (i) cavi_oracle.c against the golden vectors produced by the reference's own
+coreDualLoop (tests/golden, bit-exact) and, where oracle/_ref is present, against that library live;
+(ii) dual == primal == blocked forms; (iii) the restated R outer loop obeys the reference's own invariants."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from problems import make_problem, sweep_inputs
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "coredualloop_*.npz")))
+
+
+def _dual_inputs(d):
+    X, Y = d["X"], d["Y"]
+    gam, mu = np.array(d["gam"], order="F"), np.array(d["mu"], order="F")
+    beta = np.asfortranarray(gam * mu)
+    cp_X, cp_Y_X = np.asfortranarray(X.T @ X), np.asfortranarray(Y.T @ X)
+    return gam, mu, beta, cp_X, cp_Y_X, np.asfortranarray(cp_X @ beta)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[14:-4] for p in GOLDEN])
+def test_dual_oracle_matches_reference_golden_bit_exact(oracle_built, path):
+    native = oracle_built
+    d = dict(np.load(path))
+    q = d["Y"].shape[1]
+    gam, mu, beta, cp_X, cp_Y_X, cbx = _dual_inputs(d)
+    native.core_dual_loop(cp_X, cp_Y_X, gam, np.asfortranarray(d["log_Phi"]), np.asfortranarray(d["log_1_min_Phi"]),
+                          float(d["log_sig2_inv"]), d["log_tau"], beta, cbx, mu, d["sig2_beta"], d["tau"], d["order"],
+                          np.arange(q, dtype=np.int32), c=float(d["c"]), impl="oracle")
+    assert np.array_equal(gam, d["out_gam"])
+    assert np.array_equal(mu, d["out_mu"])
+    assert np.array_equal(beta, d["out_beta"])
+    assert np.array_equal(cbx, d["out_cp_betaX_X"])
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[14:-4] for p in GOLDEN])
+@pytest.mark.parametrize("form", ["primal", "blocked"])
+def test_sample_space_forms_match_golden(oracle_built, path, form):
+    native = oracle_built
+    d = dict(np.load(path))
+    X, Y = np.asfortranarray(d["X"]), np.asfortranarray(d["Y"])
+    gam, mu = np.array(d["gam"], order="F"), np.array(d["mu"], order="F")
+    beta = np.asfortranarray(gam * mu)
+    R = native.residual(X, Y, beta)
+    args = (gam, np.asfortranarray(d["log_Phi"]), np.asfortranarray(d["log_1_min_Phi"]), float(d["log_sig2_inv"]),
+            d["log_tau"], beta, mu, d["sig2_beta"], d["tau"], d["order"])
+    if form == "primal":
+        native.sweep_primal(X, np.asfortranarray((X ** 2).sum(0)), R, *args, c=float(d["c"]), nthreads=3)
+    else:
+        native.sweep_primal_blocked(X, R, *args, c=float(d["c"]), B=8)
+    assert np.abs(gam - d["out_gam"]).max() <= 1e-12
+    assert np.abs(mu - d["out_mu"]).max() <= 1e-12
+    # the residual carries the reference's running X'X beta:  X'(Y - R) == cp_betaX_X
+    np.testing.assert_allclose(X.T @ (Y - R), d["out_cp_betaX_X"], atol=1e-9)
+
+
+def test_dual_oracle_matches_live_reference_library(oracle_built):
+    native = oracle_built
+    if not native.ref_available():
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    X, Y, hyper, init = make_problem(120, 90, 25)
+    si = sweep_inputs(X, Y, init, c=0.8)
+    order = np.random.default_rng(1).permutation(X.shape[1]).astype(np.int32)
+    outs = {}
+    for impl in ("oracle", "reference"):
+        d = dict(X=X, Y=Y, gam=si["gam"], mu=si["mu"])
+        gam, mu, beta, cp_X, cp_Y_X, cbx = _dual_inputs(d)
+        native.core_dual_loop(cp_X, cp_Y_X, gam, si["log_Phi"], si["log_1_min_Phi"], si["log_sig2_inv"], si["log_tau"],
+                              beta, cbx, mu, si["sig2_beta"], si["tau"], order, np.arange(Y.shape[1], dtype=np.int32),
+                              c=0.8, impl=impl)
+        outs[impl] = (gam, mu, beta, cbx)
+    for a, b in zip(outs["oracle"], outs["reference"]):
+        assert np.array_equal(a, b)
+
+
+def test_sample_q_subset_only_touches_its_columns(oracle_built):
+    native = oracle_built
+    X, Y, hyper, init = make_problem(60, 30, 10)
+    si = sweep_inputs(X, Y, init)
+    d = dict(X=X, Y=Y, gam=si["gam"], mu=si["mu"])
+    gam, mu, beta, cp_X, cp_Y_X, cbx = _dual_inputs(d)
+    g0 = gam.copy()
+    native.core_dual_loop(cp_X, cp_Y_X, gam, si["log_Phi"], si["log_1_min_Phi"], si["log_sig2_inv"], si["log_tau"], beta,
+                          cbx, mu, si["sig2_beta"], si["tau"], np.arange(X.shape[1], dtype=np.int32),
+                          np.array([2, 7], dtype=np.int32), c=1.0)
+    changed = np.flatnonzero(np.any(gam != g0, axis=0))
+    assert list(changed) == [2, 7]
+
+
+@pytest.mark.parametrize("anneal", [None, (1, 2, 10)])
+def test_restated_r_loop_invariants(oracle_built, anneal):
+    """tests/testthat/main.R recipe (n=100, p=75, q=20, p0=c(5,25)): converges (test_convergence.R:5-7) and the
+    ELBO never decreases after annealing (debug stop, R/atlasqtl_global_local_core.R:359-360)."""
+    from oracle import vb_oracle
+    X, Y, hyper, init = make_problem(100, 75, 20, p_act=10, q_act=20, maf=0.2, p0=(5, 25))
+    tr = []
+    out = vb_oracle.atlasqtl_global_local_core_(Y, X, Y.shape[1], anneal, 1, 0.1, 1000, hyper, init, sweep="dual",
+                                                debug=True, trace=tr)
+    assert out["converged"]
+    lbs = [r["lb"] for r in tr if r["lb"] is not None]
+    assert all(b + 1.49e-8 >= a for a, b in zip(lbs, lbs[1:]))
+    if anneal is not None:
+        assert all(r["lb"] is None for r in tr[: anneal[2] - 1])  # no ELBO while annealing
+        np.testing.assert_allclose([r["c"] for r in tr[:10]], 2.0 ** (-(9 - np.arange(10)) / 9), rtol=1e-14)
+
+
+def test_q_approx_vec_and_bfdr():
+    from scipy import integrate
+
+    from oracle import vb_oracle
+    x = np.array([0.05, 0.7, 1.0, 1.3, 4.0, 60.0])
+    ref = [integrate.quad(lambda t: np.exp(-xx * t) / (1 + t), 0, np.inf)[0] for xx in x]  # E1(x) e^x
+    np.testing.assert_allclose(vb_oracle.Q_approx_vec(x), ref, rtol=2e-7)
+    ppi = np.array([[0.9, 0.2], [0.99, 0.6]])
+    fdr = vb_oracle.assign_bFDR(ppi)
+    np.testing.assert_allclose(fdr, [[(0.01 + 0.1) / 2, (0.01 + 0.1 + 0.4 + 0.8) / 4], [0.01, (0.01 + 0.1 + 0.4) / 3]])
