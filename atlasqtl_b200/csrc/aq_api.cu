@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/atlasqtl_b200.h"
+#include "aq_internal.h"
 #include "aq_stream.cuh"
 #include "aq_sweep.cuh"
 
@@ -197,6 +198,39 @@ int retile(aq_ctx* c) {
 }
 
 }  // namespace
+
+namespace aq {
+
+int internal_load_state(aq_ctx* c, const double* gam_vb, const double* mu_beta_vb) {
+    if (!c || !gam_vb || !mu_beta_vb) return fail(AQ_EINVAL, "internal_load_state: NULL argument");
+    AQ_CUDA(cudaSetDevice(c->device));
+    int rc = upload_pxq(c, gam_vb, c->gam);
+    if (rc != AQ_OK) return rc;
+    rc = upload_pxq(c, mu_beta_vb, c->mu);
+    if (rc != AQ_OK) return rc;
+    AQ_CUDA(cudaMemcpyAsync(c->resid, c->ymat, sizeof(double) * (size_t)c->q_pad * c->cfg.n_pad, cudaMemcpyDeviceToDevice,
+                            c->stream));
+    AQ_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_state = true;
+    return AQ_OK;
+}
+
+int internal_load_dtab(aq_ctx* c, const double* d_host) {
+    if (!c || !d_host) return fail(AQ_EINVAL, "internal_load_dtab: NULL argument");
+    AQ_CUDA(cudaSetDevice(c->device));
+    int rc = upload_pxq(c, d_host, c->dtab);
+    if (rc != AQ_OK) return rc;
+    const size_t pq = (size_t)c->p_pad * c->q_pad;
+    AQ_CUDA(cudaMemsetAsync(c->wtab, 0, sizeof(double) * pq, c->stream));
+    AQ_CUDA(cudaMemsetAsync(c->i0tab, 0, sizeof(double) * pq, c->stream));
+    AQ_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_tables = true;
+    return AQ_OK;
+}
+
+int internal_fail(int code, const char* msg) { return fail(code, msg); }
+
+}  // namespace aq
 
 extern "C" {
 

@@ -1,17 +1,135 @@
 // Stateless compatibility entry: the reference's 15-argument coreDualLoop contract
-// (src/coreLoop.cpp:38-52) served by the sample-space CUDA sweep.  See aq_coreDualLoop in
-// include/atlasqtl_b200.h.
-#include <string>
+// (src/coreLoop.cpp:38-52; .Call glue src/RcppExports.cpp:17-38) served by the sample-space CUDA sweep.
+//
+// The reference hands over Gram quantities only (cp_X = X'X, cp_Y_X = Y'X, cp_betaX_X = X'X beta).  Any
+// X~ with X~'X~ = cp_X reproduces every statistic the loop forms, so:
+//   1. pivoted Cholesky  P' cp_X P = L L'  (rank r <= n - 1), X~ = L'  (r "pseudo-samples" x p);
+//   2. residual R~ (r x q) from the pivot rows:  L_1 R~ = (cp_Y_X' - cp_betaX_X)[pivots, ]  (forward solve), so that
+//      X~' R~ = X'Y - X'X beta, i.e. exactly the running cross-products the caller passed in;
+//   3. one CUDA sweep on (X~, R~) with beta_old = m1_beta and D = log_1_min_Phi - log_Phi;
+//   4. outputs in place: gam_vb, mu_beta_vb, m1_beta = gam * mu, cp_betaX_X = cp_Y_X' - L R~_new.
+// Cost of 1./2./4. is O(p^2 r + p r q) on the host per call, so this is a parity / compatibility entry for the
+// sizes where the reference itself can run (its p x p inputs exist), not the fast path.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
 
-#include "../../include/atlasqtl_b200.h"
+#include "aq_internal.h"
+
+using aq::internal_fail;
 
 extern "C" int aq_coreDualLoop(int device, int p, int q, const double* cp_X, const double* cp_Y_X, double* gam_vb,
                                const double* log_Phi_theta_plus_zeta, const double* log_1_min_Phi_theta_plus_zeta,
                                double log_sig2_inv_vb, const double* log_tau_vb, double* m1_beta, double* cp_betaX_X,
                                double* mu_beta_vb, const double* sig2_beta_vb, const double* tau_vb,
                                const int32_t* shuffled_ind, int n_ind, const int32_t* sample_q, int n_q, double c) {
-    (void)device; (void)p; (void)q; (void)cp_X; (void)cp_Y_X; (void)gam_vb; (void)log_Phi_theta_plus_zeta;
-    (void)log_1_min_Phi_theta_plus_zeta; (void)log_sig2_inv_vb; (void)log_tau_vb; (void)m1_beta; (void)cp_betaX_X;
-    (void)mu_beta_vb; (void)sig2_beta_vb; (void)tau_vb; (void)shuffled_ind; (void)n_ind; (void)sample_q; (void)n_q; (void)c;
-    return AQ_EUNSUPPORTED;  // TODO(round 1, later today): pivoted-Cholesky pseudo-design path
+    if (!cp_X || !cp_Y_X || !gam_vb || !log_Phi_theta_plus_zeta || !log_1_min_Phi_theta_plus_zeta || !log_tau_vb ||
+        !m1_beta || !cp_betaX_X || !mu_beta_vb || !sig2_beta_vb || !tau_vb || !shuffled_ind || !sample_q)
+        return internal_fail(AQ_EINVAL, "aq_coreDualLoop: NULL argument");
+    if (p < 1 || q < 1 || n_q < 0 || n_q > q) return internal_fail(AQ_EINVAL, "aq_coreDualLoop: bad dimensions");
+    if (n_ind != p) return internal_fail(AQ_EUNSUPPORTED, "aq_coreDualLoop: shuffled_ind must visit every SNP once");
+    if (n_q == 0) return AQ_OK;
+    std::vector<char> seen(q, 0);
+    for (int a = 0; a < n_q; ++a) {
+        if (sample_q[a] < 0 || sample_q[a] >= q || seen[sample_q[a]])
+            return internal_fail(AQ_EINVAL, "aq_coreDualLoop: sample_q must hold distinct trait indices in 0..q-1");
+        seen[sample_q[a]] = 1;
+    }
+    const size_t P = (size_t)p;
+    // ---- 1. pivoted Cholesky of cp_X (column-major, symmetric PSD); L stored column-major p x r in pivoted row order
+    std::vector<double> diag(p), L;
+    std::vector<int> piv(p);
+    double dmax0 = 0.0;
+    for (int j = 0; j < p; ++j) {
+        diag[j] = cp_X[j + j * P];
+        piv[j] = j;
+        dmax0 = std::max(dmax0, diag[j]);
+    }
+    if (!(dmax0 > 0.0)) return internal_fail(AQ_EINVAL, "aq_coreDualLoop: cp_X has no positive diagonal entry");
+    const double tol = 1e-13 * dmax0;
+    const int rmax = std::min(p, 1008);
+    L.assign(P * rmax, 0.0);
+    int r = 0;
+    for (; r < rmax; ++r) {
+        int best = r;
+        for (int i = r + 1; i < p; ++i)
+            if (diag[piv[i]] > diag[piv[best]]) best = i;
+        if (diag[piv[best]] <= tol) break;
+        std::swap(piv[r], piv[best]);
+        for (int k = 0; k < r; ++k) std::swap(L[r + k * P], L[best + k * P]);
+        const int jr = piv[r];
+        const double lrr = std::sqrt(diag[jr]);
+        L[r + r * P] = lrr;
+        for (int i = r + 1; i < p; ++i) {
+            const int ji = piv[i];
+            double v = cp_X[ji + jr * P];
+            for (int k = 0; k < r; ++k) v -= L[i + k * P] * L[r + k * P];
+            v /= lrr;
+            L[i + r * P] = v;
+            diag[ji] -= v * v;
+        }
+    }
+    if (r == rmax && r < p) {
+        double rest = 0.0;
+        for (int i = r; i < p; ++i) rest = std::max(rest, diag[piv[i]]);
+        if (rest > tol) return internal_fail(AQ_EUNSUPPORTED, "aq_coreDualLoop: rank of cp_X exceeds 1008");
+    }
+    if (r < 2) return internal_fail(AQ_EUNSUPPORTED, "aq_coreDualLoop: rank of cp_X below 2");
+    // ---- X~ = L' in ORIGINAL SNP order: column j of X~ (r values) = row of L whose pivot is j
+    std::vector<double> Xt((size_t)r * p);
+    for (int i = 0; i < p; ++i)
+        for (int k = 0; k < r; ++k) Xt[k + (size_t)piv[i] * r] = L[i + k * P];
+    // ---- 2. residual from the caller's running cross-products (forward solve with the r x r pivot block)
+    std::vector<double> Rt((size_t)r * n_q), gs(P * n_q), ms(P * n_q), ds(P * n_q);
+    std::vector<double> tau_s(n_q), ltau_s(n_q), sig2_s(n_q);
+    for (int a = 0; a < n_q; ++a) {
+        const int k = sample_q[a];
+        double* col = Rt.data() + (size_t)a * r;
+        for (int i = 0; i < r; ++i) {
+            const int j = piv[i];
+            double v = cp_Y_X[k + (size_t)j * q] - cp_betaX_X[j + (size_t)k * P];
+            for (int t = 0; t < i; ++t) v -= L[i + t * P] * col[t];
+            col[i] = v / L[i + i * P];
+        }
+        for (int j = 0; j < p; ++j) {
+            gs[j + (size_t)a * P] = 1.0;  // the kernel forms beta_old = gam_old * mu_old: carry m1_beta exactly
+            ms[j + (size_t)a * P] = m1_beta[j + (size_t)k * P];
+            ds[j + (size_t)a * P] = log_1_min_Phi_theta_plus_zeta[j + (size_t)k * P] - log_Phi_theta_plus_zeta[j + (size_t)k * P];
+        }
+        tau_s[a] = tau_vb[k];
+        ltau_s[a] = log_tau_vb[k];
+        sig2_s[a] = sig2_beta_vb[k];
+    }
+    // ---- 3. the CUDA sweep
+    aq_ctx* ctx = nullptr;
+    int rc = aq_create(&ctx, device, r, p, n_q, Xt.data(), Rt.data());
+    if (rc != AQ_OK) return rc;
+    rc = aq_set_order(ctx, shuffled_ind);
+    if (rc == AQ_OK) rc = aq::internal_load_state(ctx, gs.data(), ms.data());
+    if (rc == AQ_OK) rc = aq::internal_load_dtab(ctx, ds.data());
+    if (rc == AQ_OK)
+        rc = aq_sweep(ctx, c, log_sig2_inv_vb, tau_s.data(), ltau_s.data(), sig2_s.data(), nullptr, nullptr, nullptr,
+                      nullptr, nullptr);
+    if (rc == AQ_OK) rc = aq_get_state(ctx, gs.data(), ms.data(), ds.data());  // ds <- beta
+    if (rc == AQ_OK) rc = aq_get_residual(ctx, Rt.data());
+    aq_destroy(ctx);
+    if (rc != AQ_OK) return rc;
+    // ---- 4. outputs, in place, only for the swept traits
+    for (int a = 0; a < n_q; ++a) {
+        const int k = sample_q[a];
+        const double* col = Rt.data() + (size_t)a * r;
+        for (int j = 0; j < p; ++j) {
+            gam_vb[j + (size_t)k * P] = gs[j + (size_t)a * P];
+            mu_beta_vb[j + (size_t)k * P] = ms[j + (size_t)a * P];
+            m1_beta[j + (size_t)k * P] = ds[j + (size_t)a * P];
+        }
+        for (int i = 0; i < p; ++i) {  // cp_betaX_X = X'Y - X~' R~
+            double v = 0.0;
+            for (int t = 0; t < r; ++t) v += L[i + t * P] * col[t];
+            const int j = piv[i];
+            cp_betaX_X[j + (size_t)k * P] = cp_Y_X[k + (size_t)j * q] - v;
+        }
+    }
+    return AQ_OK;
 }

@@ -1,0 +1,135 @@
+/*
+ * .Call shim between R and libatlasqtl_b200.so (include/atlasqtl_b200.h).
+ *
+ * Replaces the generated RcppEigen glue of the reference (src/RcppExports.cpp:17-74) for the CAVI sweep:
+ * plain R C API only (no Rcpp, no Eigen), one SEXP wrapper per C-ABI entry point, the context held in
+ * an external pointer with a finalizer, errors raised with Rf_error() AFTER the C call has returned
+ * (the library never throws and keeps no sticky CUDA error).
+ *
+ * Build inside the atlasqtl package (src/):   PKG_LIBS = -L<dir> -latlasqtl_b200
+ * NOT compiled in this repository's image (no R headers there): it is deliberately logic-free so that
+ * everything that can be tested is tested through the C ABI itself.
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+
+#include "atlasqtl_b200.h"
+
+static void ctx_finalizer(SEXP ptr) {
+  aq_ctx* c = (aq_ctx*)R_ExternalPtrAddr(ptr);
+  if (c) { aq_destroy(c); R_ClearExternalPtr(ptr); }
+}
+static aq_ctx* get_ctx(SEXP ptr) {
+  aq_ctx* c = (aq_ctx*)R_ExternalPtrAddr(ptr);
+  if (!c) Rf_error("atlasqtl_b200: context already destroyed");
+  return c;
+}
+static void check(int rc) { if (rc != AQ_OK) Rf_error("atlasqtl_b200 (%d): %s", rc, aq_last_error()); }
+static double* dbl_or_null(SEXP x) { return Rf_isNull(x) ? NULL : REAL(x); }
+
+/* aq_create(X, Y, device): X n x p, Y n x q double matrices (storage mode checked like Eigen::Map does) */
+SEXP _atlasqtl_aq_create(SEXP X, SEXP Y, SEXP device) {
+  if (!Rf_isReal(X) || !Rf_isReal(Y) || !Rf_isMatrix(X) || !Rf_isMatrix(Y)) Rf_error("X and Y must be double matrices");
+  int n = Rf_nrows(X), p = Rf_ncols(X), q = Rf_ncols(Y);
+  if (Rf_nrows(Y) != n) Rf_error("X and Y must have the same number of rows");
+  aq_ctx* c = NULL;
+  check(aq_create(&c, Rf_asInteger(device), n, p, q, REAL(X), REAL(Y)));
+  SEXP ptr = PROTECT(R_MakeExternalPtr(c, R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(ptr, ctx_finalizer, TRUE);
+  UNPROTECT(1);
+  return ptr;
+}
+SEXP _atlasqtl_aq_destroy(SEXP ptr) { ctx_finalizer(ptr); return R_NilValue; }
+
+/* shuffled_ind: integer vector, 0-based (as.integer(0:(p-1)) in the reference) or NULL */
+SEXP _atlasqtl_aq_set_order(SEXP ptr, SEXP shuffled_ind) {
+  check(aq_set_order(get_ctx(ptr), Rf_isNull(shuffled_ind) ? NULL : (const int32_t*)INTEGER(shuffled_ind)));
+  return R_NilValue;
+}
+
+static SEXP sums_list(int q, int with_z, double** out) {
+  const char* names[] = {"colsum_gam", "colsum_gam_mu2", "colsum_beta2", "resid_sq", "colsum_zpart"};
+  int k = with_z ? 5 : 4;
+  SEXP res = PROTECT(Rf_allocVector(VECSXP, k)), nm = PROTECT(Rf_allocVector(STRSXP, k));
+  for (int i = 0; i < k; ++i) {
+    SEXP v = PROTECT(Rf_allocVector(REALSXP, q));
+    out[i] = REAL(v);
+    SET_VECTOR_ELT(res, i, v);
+    SET_STRING_ELT(nm, i, Rf_mkChar(names[i]));
+    UNPROTECT(1);
+  }
+  Rf_setAttrib(res, R_NamesSymbol, nm);
+  UNPROTECT(2);
+  return res;
+}
+
+SEXP _atlasqtl_aq_set_state(SEXP ptr, SEXP gam_vb, SEXP mu_beta_vb) {
+  aq_ctx* c = get_ctx(ptr);
+  int q = Rf_ncols(gam_vb);
+  double* o[5];
+  SEXP res = PROTECT(sums_list(q, 0, o));
+  check(aq_set_state(c, REAL(gam_vb), REAL(mu_beta_vb), o[0], o[1], o[2], o[3]));
+  UNPROTECT(1);
+  return res;
+}
+
+/* In place on caller-allocated p x q matrices, like coreDualLoop's in-place outputs (src/coreLoop.cpp:40,45-47) */
+SEXP _atlasqtl_aq_get_state(SEXP ptr, SEXP gam_vb, SEXP mu_beta_vb, SEXP beta_vb) {
+  check(aq_get_state(get_ctx(ptr), dbl_or_null(gam_vb), dbl_or_null(mu_beta_vb), dbl_or_null(beta_vb)));
+  return R_NilValue;
+}
+
+SEXP _atlasqtl_aq_refresh_tables(SEXP ptr, SEXP theta_vb, SEXP zeta_vb, SEXP c_next, SEXP want_elbo) {
+  double part = NA_REAL;
+  check(aq_refresh_tables(get_ctx(ptr), REAL(theta_vb), REAL(zeta_vb), Rf_asReal(c_next),
+                          Rf_asLogical(want_elbo) ? &part : NULL));
+  return Rf_ScalarReal(part);
+}
+
+SEXP _atlasqtl_aq_sweep(SEXP ptr, SEXP c, SEXP log_sig2_inv_vb, SEXP tau_vb, SEXP log_tau_vb, SEXP sig2_beta_vb) {
+  aq_ctx* ctx = get_ctx(ptr);
+  int q = Rf_length(tau_vb);
+  double* o[5];
+  SEXP res = PROTECT(sums_list(q, 1, o));
+  check(aq_sweep(ctx, Rf_asReal(c), Rf_asReal(log_sig2_inv_vb), REAL(tau_vb), REAL(log_tau_vb), REAL(sig2_beta_vb),
+                 o[0], o[1], o[2], o[3], o[4]));
+  UNPROTECT(1);
+  return res;
+}
+
+SEXP _atlasqtl_aq_rowsums_zpart(SEXP ptr, SEXP p) {
+  SEXP v = PROTECT(Rf_allocVector(REALSXP, Rf_asInteger(p)));
+  check(aq_rowsums_zpart(get_ctx(ptr), REAL(v)));
+  UNPROTECT(1);
+  return v;
+}
+
+/* Stateless drop-in with the reference's exact 15 arguments (src/RcppExports.cpp:17). */
+SEXP _atlasqtl_coreDualLoop(SEXP cp_X, SEXP cp_Y_X, SEXP gam_vb, SEXP log_Phi, SEXP log_1_min_Phi, SEXP log_sig2_inv_vb,
+                            SEXP log_tau_vb, SEXP m1_beta, SEXP cp_betaX_X, SEXP mu_beta_vb, SEXP sig2_beta_vb,
+                            SEXP tau_vb, SEXP shuffled_ind, SEXP sample_q, SEXP c) {
+  int p = Rf_nrows(gam_vb), q = Rf_ncols(gam_vb);
+  check(aq_coreDualLoop(0, p, q, REAL(cp_X), REAL(cp_Y_X), REAL(gam_vb), REAL(log_Phi), REAL(log_1_min_Phi),
+                        Rf_asReal(log_sig2_inv_vb), REAL(log_tau_vb), REAL(m1_beta), REAL(cp_betaX_X), REAL(mu_beta_vb),
+                        REAL(sig2_beta_vb), REAL(tau_vb), (const int32_t*)INTEGER(shuffled_ind), Rf_length(shuffled_ind),
+                        (const int32_t*)INTEGER(sample_q), Rf_length(sample_q), Rf_asReal(c)));
+  return R_NilValue;
+}
+
+static const R_CallMethodDef CallEntries[] = {
+    {"_atlasqtl_aq_create", (DL_FUNC)&_atlasqtl_aq_create, 3},
+    {"_atlasqtl_aq_destroy", (DL_FUNC)&_atlasqtl_aq_destroy, 1},
+    {"_atlasqtl_aq_set_order", (DL_FUNC)&_atlasqtl_aq_set_order, 2},
+    {"_atlasqtl_aq_set_state", (DL_FUNC)&_atlasqtl_aq_set_state, 3},
+    {"_atlasqtl_aq_get_state", (DL_FUNC)&_atlasqtl_aq_get_state, 4},
+    {"_atlasqtl_aq_refresh_tables", (DL_FUNC)&_atlasqtl_aq_refresh_tables, 5},
+    {"_atlasqtl_aq_sweep", (DL_FUNC)&_atlasqtl_aq_sweep, 6},
+    {"_atlasqtl_aq_rowsums_zpart", (DL_FUNC)&_atlasqtl_aq_rowsums_zpart, 2},
+    {"_atlasqtl_coreDualLoop", (DL_FUNC)&_atlasqtl_coreDualLoop, 15},
+    {NULL, NULL, 0}};
+
+void R_init_atlasqtl(DllInfo* dll) { /* same registration as src/RcppExports.cpp:71-74 */
+  R_registerRoutines(dll, NULL, CallEntries, NULL, NULL);
+  R_useDynamicSymbols(dll, FALSE);
+}
