@@ -34,22 +34,30 @@ int fail(int code, const std::string& msg) {
         }                                                                                               \
     } while (0)
 
-// ---- kernel configurations (SweepCfg<WS, WT, MT, NT>): picked by n at aq_create time.
-// 9 MMA warps split the samples (n_pad = 72 NT); each holds MT 8-trait tiles: MT * NT * 2 accumulator doubles.
+// ---- kernel configurations (SweepCfg<WS, WT, MT, NT, clustered>): picked by n at aq_create time.
+// 9 MMA warps split a CTA's samples (72 NT of them); each holds MT 8-trait tiles: MT * NT * 2 accumulator doubles.
+// n <= 1008: one CTA per trait tile.  n > 1008: a thread-block cluster of 2 / 4 / 8 CTAs splits the samples.
 using CfgN1008 = SweepCfg<9, 1, 2, 14>;  // n <= 1008, 16 traits / tile
 using CfgN720 = SweepCfg<9, 1, 3, 10>;   // n <= 720,  24 traits / tile
 using CfgN504 = SweepCfg<9, 1, 4, 7>;    // n <= 504,  32 traits / tile
 using CfgN360 = SweepCfg<9, 1, 6, 5>;    // n <= 360,  48 traits / tile
 using CfgN216 = SweepCfg<9, 1, 8, 3>;    // n <= 216,  64 traits / tile
 using CfgN144 = SweepCfg<9, 1, 8, 2>;    // n <= 144,  64 traits / tile
+using CfgC7 = SweepCfg<9, 1, 4, 7, true>;    // clustered: 504 samples per CTA, 32 traits / tile
+using CfgC8 = SweepCfg<9, 1, 3, 8, true>;    // 576, 24
+using CfgC9 = SweepCfg<9, 1, 3, 9, true>;    // 648, 24
+using CfgC10 = SweepCfg<9, 1, 2, 10, true>;  // 720, 16
+using CfgC11 = SweepCfg<9, 1, 2, 11, true>;  // 792, 16
+using CfgC12 = SweepCfg<9, 1, 2, 12, true>;  // 864, 16
 
 struct CfgInfo {
-    int id, n_pad, xs, kT, threads;
+    int id, n_pad, xs, kT, threads;   // n_pad: samples per CTA (slice), padded
     size_t smem, tile_doubles;
+    int ncta;                         // CTAs per cluster (sample slices)
 };
 template <class C>
-CfgInfo info(int id) {
-    return CfgInfo{id, C::kNPad, C::kXS, C::kT, C::kThreads, C::kSmemBytes, C::kTileDoubles};
+CfgInfo info(int id, int ncta = 1) {
+    return CfgInfo{id, C::kNPad, C::kXS, C::kT, C::kThreads, C::kSmemBytes, C::kTileDoubles, ncta};
 }
 
 bool pick_cfg(int n, CfgInfo* out) {
@@ -59,7 +67,21 @@ bool pick_cfg(int n, CfgInfo* out) {
     else if (n <= 504) *out = info<CfgN504>(2);
     else if (n <= 720) *out = info<CfgN720>(1);
     else if (n <= 1008) *out = info<CfgN1008>(0);
-    else return false;
+    else {
+        int ncta = 2;
+        while (ncta <= kMaxCluster && n > ncta * 864) ncta *= 2;
+        if (ncta > kMaxCluster) return false;
+        int nt = (n + 72 * ncta - 1) / (72 * ncta);
+        if (nt < 7) nt = 7;
+        switch (nt) {
+            case 7: *out = info<CfgC7>(107, ncta); break;
+            case 8: *out = info<CfgC8>(108, ncta); break;
+            case 9: *out = info<CfgC9>(109, ncta); break;
+            case 10: *out = info<CfgC10>(110, ncta); break;
+            case 11: *out = info<CfgC11>(111, ncta); break;
+            default: *out = info<CfgC12>(112, ncta); break;
+        }
+    }
     return true;
 }
 
@@ -67,7 +89,7 @@ bool pick_cfg(int n, CfgInfo* out) {
 
 struct aq_ctx {
     int device = 0, n = 0, p = 0, q = 0;
-    int p_pad = 0, q_pad = 0, nb = 0, ntiles = 0, sm_count = 0;
+    int p_pad = 0, q_pad = 0, nb = 0, ntiles = 0, sm_count = 0, ld_resid = 0;
     CfgInfo cfg{};
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // sweep kernel
@@ -94,13 +116,36 @@ namespace {
 template <class C>
 int launch_sweep_t(aq_ctx* c, const SweepParams& P) {
     static bool attr_done[64] = {false};
+    static int max_clusters[64] = {0};
+    const int ncta = c->cfg.ncta;
+    cudaLaunchConfig_t lc{};
+    lc.blockDim = dim3(C::kThreads);
+    lc.dynamicSmemBytes = C::kSmemBytes;
+    lc.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = ncta;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    lc.attrs = attr;
+    lc.numAttrs = C::kCl ? 1 : 0;
     if (!attr_done[c->device]) {
         AQ_CUDA(cudaFuncSetAttribute(sweep_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
+        if (C::kCl) {
+            lc.gridDim = dim3(c->sm_count / ncta * ncta);
+            int nc = 0;
+            AQ_CUDA(cudaOccupancyMaxActiveClusters(&nc, sweep_kernel<C>, &lc));
+            if (nc < 1) return fail(AQ_EUNSUPPORTED, "no thread-block cluster of the required size can be scheduled");
+            max_clusters[c->device] = nc;
+        }
         attr_done[c->device] = true;
     }
-    const int grid = std::min(c->ntiles, c->sm_count);
+    int grid;
+    if (C::kCl) grid = std::min(c->ntiles, max_clusters[c->device]) * ncta;
+    else grid = std::min(c->ntiles, c->sm_count);
+    lc.gridDim = dim3(grid);
     AQ_CUDA(cudaEventRecord(c->ev0, c->stream));
-    sweep_kernel<C><<<grid, C::kThreads, C::kSmemBytes, c->stream>>>(P);
+    AQ_CUDA(cudaLaunchKernelEx(&lc, sweep_kernel<C>, P));
     AQ_CUDA(cudaGetLastError());
     AQ_CUDA(cudaEventRecord(c->ev1, c->stream));
     c->launches++;
@@ -115,7 +160,8 @@ int launch_sweep(aq_ctx* c, int mode, double cc, double log_sig2_inv) {
     P.ntiles = c->ntiles;
     P.q = c->q;
     P.q_pad = c->q_pad;
-    P.ld_resid = c->cfg.n_pad;
+    P.ld_resid = c->ld_resid;
+    P.ncta = c->cfg.ncta;
     P.resid = c->resid;
     P.gam = c->gam;
     P.mu = c->mu;
@@ -140,6 +186,12 @@ int launch_sweep(aq_ctx* c, int mode, double cc, double log_sig2_inv) {
         case 3: return launch_sweep_t<CfgN360>(c, P);
         case 4: return launch_sweep_t<CfgN216>(c, P);
         case 5: return launch_sweep_t<CfgN144>(c, P);
+        case 107: return launch_sweep_t<CfgC7>(c, P);
+        case 108: return launch_sweep_t<CfgC8>(c, P);
+        case 109: return launch_sweep_t<CfgC9>(c, P);
+        case 110: return launch_sweep_t<CfgC10>(c, P);
+        case 111: return launch_sweep_t<CfgC11>(c, P);
+        case 112: return launch_sweep_t<CfgC12>(c, P);
     }
     return fail(AQ_EUNSUPPORTED, "no kernel configuration");
 }
@@ -188,10 +240,10 @@ int fetch_outputs(aq_ctx* c, double* o0, double* o1, double* o2, double* o3, dou
 
 int retile(aq_ctx* c) {
     AQ_CUDA(cudaMemcpyAsync(c->order_dev, c->order.data(), sizeof(int32_t) * c->p, cudaMemcpyHostToDevice, c->stream));
-    build_tiles_kernel<<<c->nb, 256, 0, c->stream>>>(c->xraw, c->order_dev, c->n, c->p, c->cfg.xs, c->cfg.tile_doubles,
-                                                     c->xtiles);
+    build_tiles_kernel<<<dim3(c->nb, c->cfg.ncta), 256, 0, c->stream>>>(c->xraw, c->order_dev, c->n, c->p, c->cfg.xs,
+                                                                         c->cfg.n_pad, c->cfg.tile_doubles, c->xtiles);
     AQ_CUDA(cudaGetLastError());
-    gram_band_kernel<<<c->nb, 128, 0, c->stream>>>(c->xtiles, c->cfg.n_pad, c->cfg.xs, c->cfg.tile_doubles);
+    gram_band_kernel<<<c->nb, 128, 0, c->stream>>>(c->xtiles, c->cfg.n_pad, c->cfg.ncta, c->cfg.xs, c->cfg.tile_doubles);
     AQ_CUDA(cudaGetLastError());
     c->launches += 2;
     return AQ_OK;
@@ -208,7 +260,7 @@ int internal_load_state(aq_ctx* c, const double* gam_vb, const double* mu_beta_v
     if (rc != AQ_OK) return rc;
     rc = upload_pxq(c, mu_beta_vb, c->mu);
     if (rc != AQ_OK) return rc;
-    AQ_CUDA(cudaMemcpyAsync(c->resid, c->ymat, sizeof(double) * (size_t)c->q_pad * c->cfg.n_pad, cudaMemcpyDeviceToDevice,
+    AQ_CUDA(cudaMemcpyAsync(c->resid, c->ymat, sizeof(double) * (size_t)c->q_pad * c->ld_resid, cudaMemcpyDeviceToDevice,
                             c->stream));
     AQ_CUDA(cudaStreamSynchronize(c->stream));
     c->have_state = true;
@@ -275,7 +327,7 @@ int aq_create(aq_ctx** out, int device, int n, int p, int q_local, const double*
     if (n < 2 || p < 1 || q_local < 1) return fail(AQ_EINVAL, "aq_create: need n >= 2, p >= 1, q >= 1");
     CfgInfo cfg;
     if (!pick_cfg(n, &cfg))
-        return fail(AQ_EUNSUPPORTED, "aq_create: n > 1008 needs the sample-split (cluster) kernel, not in this build");
+        return fail(AQ_EUNSUPPORTED, "aq_create: n > 6912 is beyond the 8-CTA sample-split cluster kernel");
     int sm = 0;
     int rc = aq_device_info(device, &sm, nullptr, nullptr);
     if (rc != AQ_OK) return rc;
@@ -289,6 +341,7 @@ int aq_create(aq_ctx** out, int device, int n, int p, int q_local, const double*
     c->p_pad = (p + kBlk - 1) / kBlk * kBlk;
     c->q_pad = (q_local + cfg.kT - 1) / cfg.kT * cfg.kT;
     c->nb = c->p_pad / kBlk;
+    c->ld_resid = cfg.n_pad * cfg.ncta;
     c->ntiles = c->q_pad / cfg.kT;
     const size_t pq = (size_t)c->p_pad * c->q_pad;
     c->stage_cols = (int)std::max<size_t>(1, std::min<size_t>((size_t)q_local, ((size_t)256 << 20) / (sizeof(double) * (size_t)p)));
@@ -303,9 +356,9 @@ int aq_create(aq_ctx** out, int device, int n, int p, int q_local, const double*
         }                                                                                 \
     } while (0)
     AQ_ALLOC(c->xraw, (size_t)n * p);
-    AQ_ALLOC(c->xtiles, (size_t)c->nb * cfg.tile_doubles);
-    AQ_ALLOC(c->ymat, (size_t)c->q_pad * cfg.n_pad);
-    AQ_ALLOC(c->resid, (size_t)c->q_pad * cfg.n_pad);
+    AQ_ALLOC(c->xtiles, (size_t)c->nb * cfg.ncta * cfg.tile_doubles);
+    AQ_ALLOC(c->ymat, (size_t)c->q_pad * c->ld_resid);
+    AQ_ALLOC(c->resid, (size_t)c->q_pad * c->ld_resid);
     AQ_ALLOC(c->gam, pq);
     AQ_ALLOC(c->mu, pq);
     AQ_ALLOC(c->dtab, pq);
@@ -328,7 +381,7 @@ int aq_create(aq_ctx** out, int device, int n, int p, int q_local, const double*
     if (e == cudaSuccess) e = cudaEventCreate(&c->evr1);
     if (e == cudaSuccess) e = cudaEventCreate(&c->evt0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->evt1);
-    if (e == cudaSuccess) e = cudaMemsetAsync(c->ymat, 0, sizeof(double) * (size_t)c->q_pad * cfg.n_pad, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->ymat, 0, sizeof(double) * (size_t)c->q_pad * c->ld_resid, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->gam, 0, sizeof(double) * pq, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->mu, 0, sizeof(double) * pq, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->dtab, 0, sizeof(double) * pq, c->stream);
@@ -339,7 +392,7 @@ int aq_create(aq_ctx** out, int device, int n, int p, int q_local, const double*
     if (e == cudaSuccess) e = cudaMemcpyAsync(c->xraw, X, sizeof(double) * (size_t)n * p, cudaMemcpyHostToDevice, c->stream);
     // Y: n x q column-major -> [q_pad][n_pad] rows (same orientation, padded leading dimension)
     if (e == cudaSuccess)
-        e = cudaMemcpy2DAsync(c->ymat, sizeof(double) * cfg.n_pad, Y, sizeof(double) * n, sizeof(double) * n, q_local,
+        e = cudaMemcpy2DAsync(c->ymat, sizeof(double) * c->ld_resid, Y, sizeof(double) * n, sizeof(double) * n, q_local,
                               cudaMemcpyHostToDevice, c->stream);
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -402,7 +455,7 @@ int aq_set_state(aq_ctx* c, const double* gam_vb, const double* mu_beta_vb, doub
     if (rc != AQ_OK) return rc;
     rc = upload_pxq(c, mu_beta_vb, c->mu);
     if (rc != AQ_OK) return rc;
-    AQ_CUDA(cudaMemcpyAsync(c->resid, c->ymat, sizeof(double) * (size_t)c->q_pad * c->cfg.n_pad, cudaMemcpyDeviceToDevice,
+    AQ_CUDA(cudaMemcpyAsync(c->resid, c->ymat, sizeof(double) * (size_t)c->q_pad * c->ld_resid, cudaMemcpyDeviceToDevice,
                             c->stream));
     rc = launch_sweep(c, /*mode=*/1, 1.0, 0.0);
     if (rc != AQ_OK) return rc;
@@ -428,7 +481,7 @@ int aq_get_residual(aq_ctx* c, double* resid) {
     if (!c || !resid) return fail(AQ_EINVAL, "NULL argument");
     if (!c->have_state) return fail(AQ_ESTATE, "aq_get_residual before aq_set_state");
     AQ_CUDA(cudaSetDevice(c->device));
-    AQ_CUDA(cudaMemcpy2DAsync(resid, sizeof(double) * c->n, c->resid, sizeof(double) * c->cfg.n_pad, sizeof(double) * c->n,
+    AQ_CUDA(cudaMemcpy2DAsync(resid, sizeof(double) * c->n, c->resid, sizeof(double) * c->ld_resid, sizeof(double) * c->n,
                               c->q, cudaMemcpyDeviceToHost, c->stream));
     AQ_CUDA(cudaStreamSynchronize(c->stream));
     return AQ_OK;

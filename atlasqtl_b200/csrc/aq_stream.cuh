@@ -5,40 +5,43 @@
 
 namespace aq {
 
-// ---------------------------------------------------------------- X tiles (one CTA per SNP block)
+// ---------------------------------------------------------------- X tiles (one CTA per SNP block x sample slice)
 // xraw: [p][n] (column j of the R matrix X contiguous).  order: sweep position -> SNP index.
+// Slice r = blockIdx.y holds samples [r * n_pad_c, (r + 1) * n_pad_c); image (b, r) sits at (b * nslice + r) * tile_stride.
 __global__ void build_tiles_kernel(const double* __restrict__ xraw, const int* __restrict__ order, int n, int p,
-                                   int xs, size_t tile_stride, double* __restrict__ tiles) {
-    const int b = blockIdx.x;
-    double* tile = tiles + (size_t)b * tile_stride;
+                                   int xs, int n_pad_c, size_t tile_stride, double* __restrict__ tiles) {
+    const int b = blockIdx.x, r = blockIdx.y, nslice = gridDim.y;
+    double* tile = tiles + ((size_t)b * nslice + r) * tile_stride;
     for (int t = 0; t < kBlk; ++t) {
         const int pos = b * kBlk + t;
         const int j = pos < p ? order[pos] : -1;
         for (int i = threadIdx.x; i < xs; i += blockDim.x) {
-            // physical slot i holds logical sample swz(i, t) (the XOR is an involution)
+            // physical slot i holds logical sample swz(i, t) (the XOR is an involution) of this slice
             const int li = swz(i, t);
-            tile[t * xs + i] = (j >= 0 && li < n) ? xraw[(size_t)j * n + li] : 0.0;
+            const int gi = r * n_pad_c + li;
+            tile[t * xs + i] = (j >= 0 && li < n_pad_c && gi < n) ? xraw[(size_t)j * n + gi] : 0.0;
         }
         if (threadIdx.x == 0) reinterpret_cast<int*>(tile + kBlk * xs + 128)[t] = j;
     }
     if (threadIdx.x < 8) reinterpret_cast<int*>(tile + kBlk * xs + 128)[8 + threadIdx.x] = 0;
 }
 
-// Gram band of block b: g[t][u] = X_t' X_u for u in block b-1 (u = 0..7) and in block b (u = 8..15).
-// 128 threads, one (t, u) pair each; reads the freshly built tiles.
-__global__ void gram_band_kernel(double* __restrict__ tiles, int n_pad, int xs, size_t tile_stride) {
+// Gram band of block b: g[t][u] = X_t' X_u for u in block b-1 (u = 0..7) and in block b (u = 8..15), over ALL sample
+// slices; written into every slice's image.  128 threads, one (t, u) pair each; reads the freshly built tiles.
+__global__ void gram_band_kernel(double* __restrict__ tiles, int n_pad_c, int nslice, int xs, size_t tile_stride) {
     const int b = blockIdx.x;
     const int t = threadIdx.x >> 4, u = threadIdx.x & 15;
-    double* tile = tiles + (size_t)b * tile_stride;
     double acc = 0.0;
     if (u >= 8 || b > 0) {
-        const double* other = (u >= 8) ? tile : tile - tile_stride;
         const int uu = u & 7;
-        const double* xt = tile + t * xs;
-        const double* xu = other + uu * xs;
-        for (int i = 0; i < n_pad; ++i) acc = fma(xt[swz(i, t)], xu[swz(i, uu)], acc);
+        const int bo = (u >= 8) ? b : b - 1;
+        for (int r = 0; r < nslice; ++r) {
+            const double* xt = tiles + ((size_t)b * nslice + r) * tile_stride + t * xs;
+            const double* xu = tiles + ((size_t)bo * nslice + r) * tile_stride + uu * xs;
+            for (int i = 0; i < n_pad_c; ++i) acc = fma(xt[swz(i, t)], xu[swz(i, uu)], acc);
+        }
     }
-    tile[kBlk * xs + t * 16 + u] = acc;
+    for (int r = 0; r < nslice; ++r) tiles[((size_t)b * nslice + r) * tile_stride + kBlk * xs + t * 16 + u] = acc;
 }
 
 // ---------------------------------------------------------------- layout transposes (32 x 32 smem tiles)

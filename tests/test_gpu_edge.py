@@ -46,7 +46,10 @@ def _cpu_sweep(native, X, Y, si, order):
     (30, 7, 3),        # p < one SNP block
     (64, 9, 65),       # p, q just past a block / tile boundary
     (144, 17, 33), (150, 40, 70), (216, 24, 64), (250, 33, 50), (360, 16, 48), (400, 20, 33),
-    (504, 25, 32), (600, 30, 25), (720, 12, 24), (800, 21, 17), (1008, 10, 16),   # every kernel configuration
+    (504, 25, 32), (600, 30, 25), (720, 12, 24), (800, 21, 17), (1008, 10, 16),   # every single-CTA configuration
+    # sample-split thread-block clusters (2 / 4 / 8 CTAs), every clustered configuration, several tiles per cluster
+    (1009, 17, 40), (1100, 20, 70), (1250, 12, 30), (1400, 16, 20), (1500, 25, 50), (1728, 9, 17),
+    (1800, 12, 40), (2500, 20, 33), (3000, 24, 50), (3456, 8, 16), (3600, 10, 30), (5000, 16, 60), (6912, 8, 24),
 ])
 def test_ragged_shapes_and_all_configs(oracle_built, n, p, q):
     from atlasqtl_b200.device import SweepContext

@@ -13,6 +13,8 @@ pytestmark = pytest.mark.gpu
     (100, 75, 20, None, "reference"),
     (200, 300, 200, (1, 2, 10), "reference"),
     (500, 400, 150, (1, 2, 10), "primal"),
+    (1500, 200, 90, (1, 2, 10), "primal"),   # 2-CTA cluster
+    (3000, 120, 40, None, "primal"),          # 4-CTA cluster
 ])
 def test_trajectory_parity(oracle_built, n, p, q, anneal, form):
     from atlasqtl_b200 import core, summarise
