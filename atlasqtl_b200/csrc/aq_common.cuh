@@ -49,6 +49,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the warp for a while when the phase is still pending)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
@@ -121,6 +133,51 @@ __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+
+// ---------------------------------------------------------------- chain math
+// 1 / (1 + exp(x)) with a short dependency chain: the in-block Gauss-Seidel recurrence is latency bound, so the
+// polynomial is evaluated in Estrin form (depth 4 instead of 11) and the reciprocal by two Newton steps on the
+// hardware seed.  |relative error| < 4e-16 on exp (degree-11 minimax-quality Taylor on |r| <= ln2/2), i.e. far
+// inside the 1e-8 bound on gam_vb.  == exp(-log1pexp(x)) of the reference (src/coreLoop.cpp:28-33, :75-77).
+__device__ __forceinline__ double fast_exp_clamped(double x) {
+    x = fmin(fmax(x, -700.0), 700.0);  // keeps 2^k * e normal; beyond, 1 / (1 + e^x) is 1 or < 1e-304 anyway
+    const double kInvLn2 = 1.4426950408889634074, kLn2Hi = 6.93147180369123816490e-01, kLn2Lo = 1.90821492927058770002e-10;
+    const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: round-to-nearest-integer trick
+    const double t = fma(x, kInvLn2, kMagic);
+    const double k = t - kMagic;
+    double r = fma(-k, kLn2Hi, x);
+    r = fma(-k, kLn2Lo, r);
+    // exp(r) = sum_{i<=11} r^i / i!   (|r| <= 0.3466: truncation 0.3466^12/12! = 6e-15 relative to 1 -> use degree 13)
+    const double r2 = r * r;
+    const double p01 = fma(r, 1.0, 1.0);
+    const double p23 = fma(r, 1.0 / 6.0, 0.5);
+    const double p45 = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    const double p67 = fma(r, 1.0 / 5040.0, 1.0 / 720.0);
+    const double p89 = fma(r, 1.0 / 362880.0, 1.0 / 40320.0);
+    const double pab = fma(r, 1.0 / 39916800.0, 1.0 / 3628800.0);
+    const double pcd = fma(r, 1.0 / 6227020800.0, 1.0 / 479001600.0);
+    const double r4 = r2 * r2;
+    const double q0 = fma(p23, r2, p01);
+    const double q1 = fma(p67, r2, p45);
+    const double q2 = fma(pab, r2, p89);
+    const double r8 = r4 * r4;
+    const double h0 = fma(q1, r4, q0);
+    const double h1 = fma(pcd, r4, q2);
+    const double e = fma(h1, r8, h0);
+    // scale by 2^k through the exponent field (k in [-1022, 1022] after the clamp)
+    const int ki = __double2loint(t);  // low word of the magic sum holds the integer k
+    return __hiloint2double(__double2hiint(e) + (ki << 20), __double2loint(e));
+}
+__device__ __forceinline__ double fast_rcp(double d) {  // d in [1, 1e308]
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e0 = fma(-d, y, 1.0);   // seed is good to ~2^-23: two Newton steps reach the rounding floor
+    y = fma(y, e0, y);
+    e0 = fma(-d, y, 1.0);
+    return fma(y, e0, y);
+}
+__device__ __forceinline__ double logistic_neg(double x) { return fast_rcp(1.0 + fast_exp_clamped(x)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---------------------------------------------------------------- normal-distribution helpers
 // log Phi(x), accurate in both tails: Phi(x) = erfc(-x/sqrt2)/2; for x < -1 go through the scaled

@@ -187,6 +187,8 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 const int stage = (int)(gbi % kStages);
                 mbar_wait(&full[stage], (uint32_t)((gbi / kStages) & 1));
                 const double* xt = tiles + stage * Cfg::kTileDoubles;
+                // kSC accumulator chains per M tile: a dependent DMMA issues every ~26 cycles, the pipe takes one per 16
+                constexpr int kSC = (MT >= 4) ? 1 : 2;
                 double sa[MT][2][2];
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) sa[mt][0][0] = sa[mt][0][1] = sa[mt][1][0] = sa[mt][1][1] = 0.0;
@@ -196,15 +198,15 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
                         dmma(sa[mt][0][0], sa[mt][0][1], acc[mt][nt][0], xb.x);
-                        dmma(sa[mt][1][0], sa[mt][1][1], acc[mt][nt][1], xb.y);
+                        dmma(sa[mt][kSC - 1][0], sa[mt][kSC - 1][1], acc[mt][nt][1], xb.y);
                     }
                 }
                 double* sp = spart + ((size_t)(gbi & 1) * WS + ws) * kT * Cfg::kSps;
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
                     double2 v;  // C fragment: S^T[trait g + 8 mt][snp 2l, 2l + 1]
-                    v.x = sa[mt][0][0] + sa[mt][1][0];
-                    v.y = sa[mt][0][1] + sa[mt][1][1];
+                    v.x = (kSC == 2) ? sa[mt][0][0] + sa[mt][1][0] : sa[mt][0][0];
+                    v.y = (kSC == 2) ? sa[mt][0][1] + sa[mt][1][1] : sa[mt][0][1];
                     *reinterpret_cast<double2*>(sp + (tr0 + mt * 8 + g) * Cfg::kSps + 2 * l) = v;
                 }
                 __syncwarp();
@@ -349,21 +351,18 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
             const double hinv = 1.0 / (2.0 * sig2);                               // :76
             const double cst = -(P.log_tau[k] + P.log_sig2_inv + log(sig2)) / 2;  // :56
             double sg = 0.0, sgm2 = 0.0, sb2 = 0.0, sz = 0.0;
-            double dprev[kBlk];
-#pragma unroll
-            for (int t = 0; t < kBlk; ++t) dprev[t] = 0.0;
             for (int b = 0; b < nb; ++b, ++gb) {
                 const int stage = (int)(gb % kStages);
                 mbar_wait(&full[stage], (uint32_t)((gb / kStages) & 1));
                 const double* xt = tiles + stage * Cfg::kTileDoubles;
                 const double* gband = xt + kBlk * XS;
                 const int* ids = reinterpret_cast<const int*>(gband + 128);
+                // all 40 loads are issued back to back (no use in between), so one DRAM/L2 round trip covers the block
                 double go[kBlk], mo[kBlk], dd[kBlk], ww[kBlk], ii[kBlk];
-                int id[kBlk];
 #pragma unroll
                 for (int t = 0; t < kBlk; ++t) {
-                    id[t] = ids[t];
-                    const size_t off = (size_t)(id[t] < 0 ? 0 : id[t]) * P.q_pad + k;
+                    const int idt = ids[t];
+                    const size_t off = (size_t)(idt < 0 ? 0 : idt) * P.q_pad + k;
                     go[t] = P.gam[off];
                     mo[t] = P.mu[off];
                     if (P.mode == 0) {
@@ -374,7 +373,10 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                         dd[t] = ww[t] = ii[t] = 0.0;
                     }
                 }
-                double s[kBlk], dl[kBlk];
+                // the previous block's -Delta row is read back from shared memory for the look-ahead correction
+                double* drow = dbuf + (size_t)(gb & 1) * kT * kBlk + tls * kBlk;
+                const double* dprow = dbuf + (size_t)((gb + 1) & 1) * kT * kBlk + tls * kBlk;
+                double s[kBlk], nd[kBlk];
                 if (P.mode == 0) {
                     mbar_wait(&sdone[gb & 1], (uint32_t)((gb >> 1) & 1));
                     const double* sp = spart + (size_t)(gb & 1) * WS * kT * Cfg::kSps + tls * Cfg::kSps;
@@ -404,38 +406,47 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     // look-ahead correction: S was formed before the previous block's update was applied
                     if (b > 0) {
 #pragma unroll
-                        for (int t = 0; t < kBlk; ++t)
+                        for (int u = 0; u < kBlk; u += 2) {
+                            const double2 nd2 = *reinterpret_cast<const double2*>(dprow + u);  // -Delta_prev[u], [u+1]
 #pragma unroll
-                            for (int u = 0; u < kBlk; ++u) s[t] = fma(-gband[t * 16 + u], dprev[u], s[t]);
+                            for (int t = 0; t < kBlk; ++t) {
+                                s[t] = fma(gband[t * 16 + u], nd2.x, s[t]);
+                                s[t] = fma(gband[t * 16 + u + 1], nd2.y, s[t]);
+                            }
+                        }
+                    }
+                    double sum_i0 = 0.0;
+#pragma unroll
+                    for (int t = 0; t < kBlk; ++t) {
+                        const bool live = ids[t] >= 0;
+                        go[t] = live ? go[t] * mo[t] : 0.0;  // beta_old (0 for padding slots: their X column is 0)
+                        s[t] = fma(go[t], gband[t * 16 + 8 + t], s[t]);  // leave-one-out: + beta_old |X_t|^2
+                        sum_i0 += live ? ii[t] : 0.0;
                     }
 #pragma unroll
                     for (int t = 0; t < kBlk; ++t) {
-                        const double bo = go[t] * mo[t];
-                        s[t] = fma(bo, gband[t * 16 + 8 + t], s[t]);  // leave-one-out: + beta_old |X_t|^2
-                    }
-#pragma unroll
-                    for (int t = 0; t < kBlk; ++t) {
-                        const double bo = go[t] * mo[t];
                         const double m = a * s[t];                                    // :73
                         const double x = P.c * (dd[t] - m * m * hinv + cst);          // :75-77
-                        const double gm = 1.0 / (1.0 + exp(x));                       // == exp(-log1pexp(x))
+                        const double gm = logistic_neg(x);                            // 1/(1+e^x) == exp(-log1pexp(x))
                         const double bn = gm * m;                                     // :79
-                        const bool live = id[t] >= 0;
-                        dl[t] = live ? bn - bo : 0.0;
+                        const double dlt = bn - go[t];                                // 0 for padding slots (m == 0)
 #pragma unroll
-                        for (int u = t + 1; u < kBlk; ++u) s[u] = fma(-gband[u * 16 + 8 + t], dl[t], s[u]);
-                        if (live) {
+                        for (int u = t + 1; u < kBlk; ++u) s[u] = fma(-gband[u * 16 + 8 + t], dlt, s[u]);
+                        nd[t] = -dlt;
+                        const int idt = ids[t];
+                        if (idt >= 0) {
                             sg += gm;
                             sgm2 = fma(gm * m, m, sgm2);
                             sb2 = fma(bn, bn, sb2);
-                            sz += fma(gm, ww[t], ii[t]);
+                            sz = fma(gm, ww[t], sz);
                             if (valid) {
-                                const size_t off = (size_t)id[t] * P.q_pad + k;
+                                const size_t off = (size_t)idt * P.q_pad + k;
                                 P.gam[off] = gm;
                                 P.mu[off] = m;
                             }
                         }
                     }
+                    sz += sum_i0;
                 } else {
                     if (gb >= 2) {  // -Delta buffer (gb & 1) free again in every CTA
                         if (kCl) mbar_wait_cluster(&dcons[gb & 1], (uint32_t)(((gb >> 1) - 1) & 1));
@@ -443,31 +454,30 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     }
 #pragma unroll
                     for (int t = 0; t < kBlk; ++t) {
-                        const bool live = id[t] >= 0;
-                        const double bo = go[t] * mo[t];
-                        dl[t] = live ? bo : 0.0;  // R = Y - X beta: subtract X_t beta_t
+                        const bool live = ids[t] >= 0;
+                        const double bo = live ? go[t] * mo[t] : 0.0;  // R = Y - X beta: subtract X_t beta_t
                         if (live) {
                             sg += go[t];
                             sgm2 = fma(go[t] * mo[t], mo[t], sgm2);
                             sb2 = fma(bo, bo, sb2);
                         }
+                        nd[t] = -bo;
                     }
                 }
+                // publish -Delta only now: a shared-memory store inside the step loop would order every later Gram-band
+                // load behind it (possible aliasing) and put the LDS latency on the serial path of each step
                 if (active) {
-                    const size_t doff = (size_t)(gb & 1) * kT * kBlk + tl * kBlk;
 #pragma unroll
                     for (int t = 0; t < kBlk; t += 2) {
                         double2 v;
-                        v.x = -dl[t];
-                        v.y = -dl[t + 1];
-                        *reinterpret_cast<double2*>(dbuf + doff + t) = v;
+                        v.x = nd[t];
+                        v.y = nd[t + 1];
+                        *reinterpret_cast<double2*>(drow + t) = v;
                         if (kCl)
                             for (int r2 = 1; r2 < ncta; ++r2)
-                                st_cluster_v2(dbuf_remote[r2] + (uint32_t)((doff + t) * sizeof(double)), v.x, v.y);
+                                st_cluster_v2(dbuf_remote[r2] + (uint32_t)(((size_t)(gb & 1) * kT * kBlk + tl * kBlk + t) * sizeof(double)), v.x, v.y);
                     }
                 }
-#pragma unroll
-                for (int t = 0; t < kBlk; ++t) dprev[t] = dl[t];
                 if (kCl) fence_cluster();
                 __syncwarp();
                 if (lane == 0) {
