@@ -94,12 +94,37 @@ __global__ void fill_kernel(double* __restrict__ x, size_t nelem, double v) {
 // Optional ELBO-B part (R/elbo.R:19-26): sum gam lp + (1-gam) lq - gam log(gam+eps) - (1-gam) log(1-gam+eps).
 // Grid: blockIdx.y strides over rows j, blockIdx.x * blockDim.x covers traits k (coalesced).
 constexpr int kTabRowsPerBlock = 8;
+
+// Everything the table pass needs about the standard normal at one point u, from ONE erfcx, ONE exp, one log and
+// one log1p:  with a = |u|/sqrt2, E = erfcx(a), e2 = exp(-u^2/2):  Q = E e2 / 2 is the tail mass beyond |u|,
+//   log Q = log(E/2) - u^2/2,  log(1-Q) = log1p(-Q),  phi/Q = sqrt(2/pi)/E  (no exp),  phi/(1-Q) = e2/(sqrt(2 pi)(1-Q)).
+struct NormalPoint {
+    double log_tail, log_body;  // log Q, log(1 - Q)
+    double r_tail, r_body;      // phi / Q, phi / (1 - Q)
+};
+__device__ __forceinline__ NormalPoint normal_point(double u, bool want_logs, bool want_ratios) {
+    const double kRs2 = 0.70710678118654752440, kSqrt2OverPi = 0.79788456080286535588, kInvSqrt2Pi = 0.39894228040143267794;
+    NormalPoint o;
+    const double a = fabs(u) * kRs2;
+    const double E = erfcx(a);
+    const double e2 = exp(-0.5 * u * u);
+    const double Q = 0.5 * E * e2;
+    if (want_logs) {
+        o.log_tail = log(0.5 * E) - 0.5 * u * u;
+        o.log_body = log1p(-Q);
+    }
+    if (want_ratios) {
+        o.r_tail = kSqrt2OverPi / E;
+        o.r_body = kInvSqrt2Pi * e2 / (1.0 - Q);
+    }
+    return o;
+}
+
 __global__ void __launch_bounds__(256) tables_kernel(const double* __restrict__ theta, const double* __restrict__ zeta, int p,
                                                      int q, int q_pad, double sqrt_c, int c_is_one,
                                                      const double* __restrict__ gam, double* __restrict__ dtab,
                                                      double* __restrict__ wtab, double* __restrict__ i0tab, int want_elbo,
                                                      double* __restrict__ partials) {
-    const double kLogSqrt2Pi = 0.91893853320467274178;
     const double eps = 1.8189894035458565e-12;  // .Machine$double.eps^0.75 (R/elbo.R:15)
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     double part = 0.0;
@@ -112,18 +137,20 @@ __global__ void __launch_bounds__(256) tables_kernel(const double* __restrict__ 
             if (j >= p) break;
             const size_t off = (size_t)j * q_pad + k;
             const double u = theta[j] + zk;
-            const double lp = log_ndtr(u), lq = log_ndtr(-u);
+            const NormalPoint nu = normal_point(u, true, c_is_one != 0);
+            const double lp = (u >= 0.0) ? nu.log_body : nu.log_tail;  // log Phi(u)
+            const double lq = (u >= 0.0) ? nu.log_tail : nu.log_body;  // log(1 - Phi(u))
             dtab[off] = lq - lp;
-            double U = u, lpU = lp, lqU = lq;
-            if (!c_is_one) {
+            double U = u, r_tail = nu.r_tail, r_body = nu.r_body;
+            if (!c_is_one) {  // update_Z_ evaluates the CDFs at sqrt(c) (theta + zeta) while annealing (R/update_vb.R:219-224)
                 U = sqrt_c * u;
-                lpU = log_ndtr(U);
-                lqU = log_ndtr(-U);
+                const NormalPoint nU = normal_point(U, false, true);
+                r_tail = nU.r_tail;
+                r_body = nU.r_body;
             }
-            const double e = -0.5 * U * U - kLogSqrt2Pi;
-            double m1 = exp(e - lpU);
-            if (m1 < -U) m1 = -U;
-            double m0 = -exp(e - lqU);
+            double m1 = (U >= 0.0) ? r_body : r_tail;    // phi(U) / Phi(U)
+            double m0 = -((U >= 0.0) ? r_tail : r_body); // -phi(U) / (1 - Phi(U))
+            if (m1 < -U) m1 = -U;                        // R/utils.R:179, :184
             if (m0 > -U) m0 = -U;
             wtab[off] = m1 - m0;
             i0tab[off] = m0;
