@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -40,9 +41,9 @@ int fail(int code, const std::string& msg) {
 using CfgN1008 = SweepCfg<9, 1, 2, 14>;  // n <= 1008, 16 traits / tile
 using CfgN720 = SweepCfg<9, 1, 3, 10>;   // n <= 720,  24 traits / tile
 using CfgN504 = SweepCfg<9, 1, 4, 7>;    // n <= 504,  32 traits / tile
-using CfgN360 = SweepCfg<9, 1, 6, 5>;    // n <= 360,  48 traits / tile
-using CfgN216 = SweepCfg<9, 1, 8, 3>;    // n <= 216,  64 traits / tile
-using CfgN144 = SweepCfg<9, 1, 8, 2>;    // n <= 144,  64 traits / tile
+using CfgN360 = SweepCfg<9, 1, 4, 5>;    // n <= 360,  32 traits / tile (one chain lane per trait)
+using CfgN216 = SweepCfg<9, 1, 4, 3>;    // n <= 216,  32 traits / tile
+using CfgN144 = SweepCfg<9, 1, 4, 2>;    // n <= 144,  32 traits / tile
 using CfgC7 = SweepCfg<9, 1, 4, 7, true>;    // clustered: 504 samples per CTA, 32 traits / tile
 using CfgC8 = SweepCfg<9, 1, 3, 8, true>;    // 576, 24
 using CfgC9 = SweepCfg<9, 1, 3, 9, true>;    // 648, 24
@@ -61,6 +62,24 @@ CfgInfo info(int id, int ncta = 1) {
 }
 
 bool pick_cfg(int n, CfgInfo* out) {
+    // development knob: AQ_FORCE_CLUSTER=2|4|8 selects the sample-split cluster kernel even where one CTA suffices
+    const char* fc = std::getenv("AQ_FORCE_CLUSTER");
+    const int force = fc ? std::atoi(fc) : 0;
+    if (force == 2 || force == 4 || force == 8) {
+        int nt = (n + 72 * force - 1) / (72 * force);
+        if (nt < 7) nt = 7;
+        if (nt <= 12) {
+            switch (nt) {
+                case 7: *out = info<CfgC7>(107, force); break;
+                case 8: *out = info<CfgC8>(108, force); break;
+                case 9: *out = info<CfgC9>(109, force); break;
+                case 10: *out = info<CfgC10>(110, force); break;
+                case 11: *out = info<CfgC11>(111, force); break;
+                default: *out = info<CfgC12>(112, force); break;
+            }
+            return true;
+        }
+    }
     if (n <= 144) *out = info<CfgN144>(5);
     else if (n <= 216) *out = info<CfgN216>(4);
     else if (n <= 360) *out = info<CfgN360>(3);
@@ -179,6 +198,18 @@ int launch_sweep(aq_ctx* c, int mode, double cc, double log_sig2_inv) {
     P.rsq = c->ovec + 3 * (size_t)c->q_pad;
     P.cs_z = c->ovec + 4 * (size_t)c->q_pad;
     P.mode = mode;
+    P.timing = nullptr;
+#ifdef AQ_TIMING
+    {
+        static long long* tbuf = nullptr;
+        if (!tbuf) { cudaMalloc(&tbuf, 16 * sizeof(long long)); }
+        long long h[16];
+        cudaMemcpy(h, tbuf, sizeof(h), cudaMemcpyDeviceToHost);
+        if (mode == 0) { fprintf(stderr, "[timing of previous sweep, cycles/block]"); for (int i = 0; i < 10; ++i) fprintf(stderr, " t%d=%lld", i, h[i] / (c->nb > 0 ? c->nb : 1)); fprintf(stderr, "\n"); }
+        cudaMemset(tbuf, 0, 16 * sizeof(long long));
+        P.timing = tbuf;
+    }
+#endif
     switch (c->cfg.id) {
         case 0: return launch_sweep_t<CfgN1008>(c, P);
         case 1: return launch_sweep_t<CfgN720>(c, P);

@@ -13,7 +13,7 @@ constexpr int kTileTail = 144;   // doubles appended to each X tile: 128 (Gram b
 // shared memory by one bulk copy:
 //   [kBlk][xs]  doubles   X columns of the block's SNPs, samples contiguous, sample index XOR-swizzled
 //                         (i ^ ((t & 2) << 1)) so that both MMA operand patterns are bank-conflict free
-//   [kBlk][16]  doubles   Gram band: g[t][0..7] = X_t' X_u, u in the PREVIOUS block; g[t][8+u] = X_t' X_u, u in this block
+//   [kBlk][16]  doubles   Gram band: g[t][0..7] = X_t' X_u, u in the NEXT block; g[t][8+u] = X_t' X_u, u in this block
 //   [kBlk]      int32     SNP index (row of the p x q arrays) of slot t, -1 for padding slots; then 8 int32 of padding
 __host__ __device__ inline size_t tile_doubles(int xs) { return (size_t)kBlk * xs + kTileTail; }
 __host__ __device__ inline int swz(int i, int t) { return i ^ ((t & 2) << 1); }
@@ -135,21 +135,23 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ---------------------------------------------------------------- chain math
-// 1 / (1 + exp(x)) with a short dependency chain: the in-block Gauss-Seidel recurrence is latency bound, so the
-// polynomial is evaluated in Estrin form (depth 4 instead of 11) and the reciprocal by two Newton steps on the
-// hardware seed.  |relative error| < 4e-16 on exp (degree-11 minimax-quality Taylor on |r| <= ln2/2), i.e. far
-// inside the 1e-8 bound on gam_vb.  == exp(-log1pexp(x)) of the reference (src/coreLoop.cpp:28-33, :75-77).
-__device__ __forceinline__ double fast_exp_clamped(double x) {
-    x = fmin(fmax(x, -700.0), 700.0);  // keeps 2^k * e normal; beyond, 1 / (1 + e^x) is 1 or < 1e-304 anyway
+// 1 / (1 + exp(x)) with a short dependency chain: the in-block Gauss-Seidel recurrence is latency bound (one fp64
+// op is ~9 cycles), so
+//   - exp(r), |r| <= ln2/2, is a degree-13 Taylor polynomial in Estrin form (depth 4 instead of 13; truncation 4e-18);
+//   - 2^k is assembled on the integer side while the polynomial runs, and 1 + 2^k e^r is ONE fma;
+//   - the reciprocal is the hardware seed (relative error e0 <= 2^-20) times (1 + e0 + e0^2): error e0^3 < 1e-18;
+//   - out-of-range arguments are resolved by selects at the end instead of clamps at the start.
+// |relative error| < 4e-16, far inside the 1e-8 bound on gam_vb.  == exp(-log1pexp(x)) of the reference
+// (src/coreLoop.cpp:28-33, :75-77).
+__device__ __forceinline__ double logistic_neg(double x) {
     const double kInvLn2 = 1.4426950408889634074, kLn2Hi = 6.93147180369123816490e-01, kLn2Lo = 1.90821492927058770002e-10;
     const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: round-to-nearest-integer trick
     const double t = fma(x, kInvLn2, kMagic);
     const double k = t - kMagic;
     double r = fma(-k, kLn2Hi, x);
     r = fma(-k, kLn2Lo, r);
-    // exp(r) = sum_{i<=11} r^i / i!   (|r| <= 0.3466: truncation 0.3466^12/12! = 6e-15 relative to 1 -> use degree 13)
     const double r2 = r * r;
-    const double p01 = fma(r, 1.0, 1.0);
+    const double p01 = r + 1.0;
     const double p23 = fma(r, 1.0 / 6.0, 0.5);
     const double p45 = fma(r, 1.0 / 120.0, 1.0 / 24.0);
     const double p67 = fma(r, 1.0 / 5040.0, 1.0 / 720.0);
@@ -163,20 +165,17 @@ __device__ __forceinline__ double fast_exp_clamped(double x) {
     const double r8 = r4 * r4;
     const double h0 = fma(q1, r4, q0);
     const double h1 = fma(pcd, r4, q2);
-    const double e = fma(h1, r8, h0);
-    // scale by 2^k through the exponent field (k in [-1022, 1022] after the clamp)
-    const int ki = __double2loint(t);  // low word of the magic sum holds the integer k
-    return __hiloint2double(__double2hiint(e) + (ki << 20), __double2loint(e));
-}
-__device__ __forceinline__ double fast_rcp(double d) {  // d in [1, 1e308]
+    const double e = fma(h1, r8, h0);  // exp(r)
+    // 2^k: the low word of the magic sum holds the integer k (|k| <= 1010 for |x| <= 700: a normal number)
+    const double scale = __hiloint2double((__double2loint(t) + 1023) << 20, 0);
+    const double d = fma(e, scale, 1.0);  // 1 + exp(x) in [1, 1e304]
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-    double e0 = fma(-d, y, 1.0);   // seed is good to ~2^-23: two Newton steps reach the rounding floor
-    y = fma(y, e0, y);
-    e0 = fma(-d, y, 1.0);
-    return fma(y, e0, y);
+    const double e0 = fma(-d, y, 1.0);
+    y = fma(y, fma(e0, e0, e0), y);
+    // beyond +-700 the function is 0 / 1 to 1e-304 and the pieces above are meaningless; NaN falls through
+    return x > 700.0 ? 0.0 : (x < -700.0 ? 1.0 : y);
 }
-__device__ __forceinline__ double logistic_neg(double x) { return fast_rcp(1.0 + fast_exp_clamped(x)); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---------------------------------------------------------------- normal-distribution helpers

@@ -26,15 +26,16 @@ __global__ void build_tiles_kernel(const double* __restrict__ xraw, const int* _
     if (threadIdx.x < 8) reinterpret_cast<int*>(tile + kBlk * xs + 128)[8 + threadIdx.x] = 0;
 }
 
-// Gram band of block b: g[t][u] = X_t' X_u for u in block b-1 (u = 0..7) and in block b (u = 8..15), over ALL sample
-// slices; written into every slice's image.  128 threads, one (t, u) pair each; reads the freshly built tiles.
+// Gram band of block b: g[t][u] = X_t' X_u for u in block b+1 (u = 0..7; zero for the last block) and in block b
+// (u = 8..15), over ALL sample slices; written into every slice's image.  128 threads, one (t, u) pair each; reads the
+// freshly built tiles.
 __global__ void gram_band_kernel(double* __restrict__ tiles, int n_pad_c, int nslice, int xs, size_t tile_stride) {
     const int b = blockIdx.x;
     const int t = threadIdx.x >> 4, u = threadIdx.x & 15;
     double acc = 0.0;
-    if (u >= 8 || b > 0) {
+    if (u >= 8 || b + 1 < (int)gridDim.x) {
         const int uu = u & 7;
-        const int bo = (u >= 8) ? b : b - 1;
+        const int bo = (u >= 8) ? b : b + 1;
         for (int r = 0; r < nslice; ++r) {
             const double* xt = tiles + ((size_t)b * nslice + r) * tile_stride + t * xs;
             const double* xu = tiles + ((size_t)bo * nslice + r) * tile_stride + uu * xs;

@@ -11,16 +11,25 @@
 //                   same registers as the A operand of  S^T = R^T X_b  -- the accumulator layout
 //                   C[m][2l+e] is an A fragment A[m][l] once the contraction index is read as 2l+e, so the
 //                   residual never moves: it is loaded once per tile and stored once per tile.
-//   1-2 "chain" warps  one lane per trait: resolve the in-block Gauss-Seidel order exactly from the Gram
-//                   band (S[t] -= G[t][u] Delta[u]), evaluate mu / gam (annealed logistic) / beta, emit
-//                   Delta and the per-trait running sums.
+//   1 "chain" warp  one lane per trait: resolves the in-block Gauss-Seidel order exactly from the Gram
+//                   band (S[u] -= G[t][u] Delta[t]), evaluates mu / gam (annealed logistic) / beta and emits
+//                   -Delta.  It is the only serial dependency of the sweep (block b+1 needs Delta_b), so it
+//                   touches shared memory only; everything else of a block is done around it by the
+//   1 "helper" warp which sums the split-K partials of S, fetches the block's beta_old and c (D + cst) from the
+//                   p x q arrays one block ahead, writes gam / mu back and keeps the per-trait running sums.
 //   1 producer warp one elected lane streams the pre-tiled X blocks (+ Gram band + SNP ids) into a
 //                   3-stage shared-memory ring with 1-D bulk copies (TMA engine) on mbarriers.
 //
 // One-block look-ahead hides the serial chain behind the tensor pipe: S'_{b+1} = X_{b+1}' R_{b-1} is formed
-// while the chain of block b runs, and corrected by the cross Gram block, S_{b+1} = S'_{b+1} - G_{b+1,b} Delta_b.
+// while the chain of block b runs, and corrected by the cross Gram block, S_{b+1} = S'_{b+1} - G_{b+1,b} Delta_b;
+// the correction is accumulated inside the chain of block b (independent FMAs that fill its latency bubbles).
 #pragma once
 #include "aq_common.cuh"
+#ifdef AQ_TIMING
+#define AQ_T(i) do { long long t_ = clock64(); if (blockIdx.x == 0 && lane == 0 && special_idx == 0 && P.timing) P.timing[i] += t_ - tlast; tlast = t_; } while (0)
+#else
+#define AQ_T(i) do { } while (0)
+#endif
 
 namespace aq {
 
@@ -50,6 +59,7 @@ struct SweepParams {
     double* rsq;
     double* cs_z;
     int mode;               // 0: sweep;  1: build residual (R -= X beta) + sums from the loaded state
+    long long* timing;      // development only (-DAQ_TIMING): per-section cycle sums of the chain warp
 };
 
 constexpr int kMaxCluster = 8;
@@ -63,7 +73,7 @@ struct SweepCfg {
     static constexpr bool kCl = CL_;  // sample-split thread-block cluster variant (n > 1008)
     static constexpr int kMmaWarps = WS * WT;
     static constexpr int kT = WT * MT * 8;           // traits per tile
-    static constexpr int kChainWarps = (kT + 31) / 32;
+    static constexpr int kChainWarps = 1;            // one lane per trait
     static constexpr int kNPad = WS * NT * 8;        // samples per CTA, padded
     static constexpr int kXS = kNPad + ((kNPad % 16 == 0) ? 8 : 0);  // tile row stride == 8 (mod 16) doubles
     static constexpr int kThreads = 12 * 32;  // warps 3, 7, 11 (SMSP 3): chain warp(s) + producer
@@ -73,17 +83,18 @@ struct SweepCfg {
     static constexpr size_t kSpartDoubles = (size_t)2 * WS * kT * kSps;
     static constexpr size_t kDbufDoubles = (size_t)2 * kT * kBlk;
     static constexpr size_t kRsqDoubles = (size_t)WS * kT;
+    static constexpr size_t kIoDoubles = (size_t)2 * kBlk * 2 * kT;  // [2][kBlk][2][kT]: in beta_old, c (D + cst); out gam, mu
     // cluster variant only: followers' reduced S tiles and squared-norm partials land in the leader's shared memory
     static constexpr size_t kRedDoubles = kCl ? (size_t)2 * (kMaxCluster - 1) * kT * kSps : 0;
     static constexpr size_t kRsqAllDoubles = kCl ? (size_t)(kMaxCluster - 1) * kT : 0;
-    static constexpr int kNumBars = 2 * kStages + 2 + 2 + 2 + 2 + 1;  // full, empty, sdone, dready, dcons, sred, rsqbar
+    static constexpr int kNumBars = 2 * kStages + 2 + 2 + 2 + 2 + 1 + 2;  // full, empty, sdone, dready, dcons, sred, rsqbar, inready
     static constexpr size_t kSmemBytes =
-        (kStages * kTileDoubles + kSpartDoubles + kDbufDoubles + kRsqDoubles + kRedDoubles + kRsqAllDoubles) * sizeof(double) +
-        16 * sizeof(uint64_t);
-    static_assert(kNumBars <= 16, "barrier block");
+        (kStages * kTileDoubles + kSpartDoubles + kDbufDoubles + kRsqDoubles + kIoDoubles + kRedDoubles + kRsqAllDoubles) *
+            sizeof(double) +
+        24 * sizeof(uint64_t);
+    static_assert(kNumBars <= 24, "barrier block");
     static_assert(kMmaWarps == 9, "9 MMA warps: three per SMSP on SMSPs 0-2");
-    static_assert(kChainWarps <= 2, "at most 64 traits per tile");
-    static_assert(!kCl || kChainWarps == 1, "cluster variant: one chain / reducer warp");
+    static_assert(kT <= 32, "one chain lane per trait");
     static_assert(kXS % 16 == 8, "row stride must be 8 mod 16 doubles");
     static_assert(kSmemBytes <= 232448, "shared memory budget (227 KB)");
 };
@@ -98,7 +109,8 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
     double* spart = tiles + kStages * Cfg::kTileDoubles;  // [2][WS][kT][kSps]
     double* dbuf = spart + Cfg::kSpartDoubles;            // [2][kT][kBlk]  (holds -Delta)
     double* rsqs = dbuf + Cfg::kDbufDoubles;              // [WS][kT]
-    double* red = rsqs + Cfg::kRsqDoubles;                // leader: [2][kMaxCluster-1][kT][kSps]
+    double* iobuf = rsqs + Cfg::kRsqDoubles;              // [2][kBlk][2][kT]
+    double* red = iobuf + Cfg::kIoDoubles;                // leader: [2][kMaxCluster-1][kT][kSps]
     double* rsq_all = red + Cfg::kRedDoubles;             // leader: [kMaxCluster-1][kT]
     uint64_t* bars = reinterpret_cast<uint64_t*>(rsq_all + Cfg::kRsqAllDoubles);
     uint64_t* full = bars;                       // [kStages]  tile landed (tx bytes)
@@ -108,12 +120,13 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
     uint64_t* dcons = bars + 2 * kStages + 4;    // [2]  mode 1 only, leader: all MMA warps consumed -Delta buffer
     uint64_t* sred = bars + 2 * kStages + 6;     // [2]  leader: followers delivered their reduced S tiles
     uint64_t* rsqbar = bars + 2 * kStages + 8;   // [1]  leader: followers delivered their squared-norm partials
+    uint64_t* inready = bars + 2 * kStages + 9;  // [2]  helper warp staged S and the block's inputs for the chain
 
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // role map: SMSP 3 (wid % 4 == 3) hosts the special warps, SMSPs 0-2 the MMA warps
     const bool is_special = (wid & 3) == 3;
     const int mma_idx = wid - (wid >> 2);   // 0..8 for MMA warps
-    const int special_idx = wid >> 2;       // 0..2 for special warps
+    const int special_idx = wid >> 2;       // special warps: 0 chain (followers: S reducer), 1 producer, 2 helper
     const int ncta = kCl ? P.ncta : 1;
     const int rank = kCl ? (int)cluster_ctarank() : 0;
     const int group = kCl ? (int)cluster_id_x() : (int)blockIdx.x;         // tile-loop index of this CTA (cluster)
@@ -125,6 +138,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
             mbar_init(&dready[s], Cfg::kChainWarps);
             mbar_init(&dcons[s], Cfg::kMmaWarps * ncta);
             mbar_init(&sred[s], ncta > 1 ? ncta - 1 : 1);
+            mbar_init(&inready[s], 1);
         }
         mbar_init(&rsqbar[0], ncta > 1 ? ncta - 1 : 1);
         fence_mbar_init();
@@ -136,7 +150,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
     const int my_tiles = (P.ntiles - group + ngroups - 1) / ngroups;
     const uint32_t tile_bytes = (uint32_t)(Cfg::kTileDoubles * sizeof(double));
 
-    if (is_special && special_idx == Cfg::kChainWarps) {
+    if (is_special && special_idx == 1) {
         // ------------------------------------------------------------------ producer
         if (lane == 0) {
             const long total = (long)my_tiles * nb;
@@ -278,7 +292,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     if (mtid < kT && k0 + mtid < P.q) P.rsq[k0 + mtid] = ss;
                 } else if (rank != 0) {
                     if (mtid < kT) st_cluster_f64(rsq_all_leader + (uint32_t)(((rank - 1) * kT + mtid) * sizeof(double)), ss);
-                    fence_cluster();
+                    // release.cluster arrive below is cumulative over the stores ordered before it by __syncwarp
                     __syncwarp();
                     if (mtid == 0) mbar_arrive_cluster(rsqbar_leader);
                 } else {
@@ -291,11 +305,11 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
             }
             asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kMmaWarps * 32) : "memory");
         }
-    } else if (special_idx < Cfg::kChainWarps && rank != 0) {
+    } else if (special_idx == 0 && rank != 0) {
         // ------------------------------------------------------------------ follower CTA: S-tile reducer warp
         // Sums this CTA's WS split-K partials and ships the kT x 8 tile into the leader's shared memory.
         if (P.mode == 0) {
-            const int tl = special_idx * 32 + lane;
+            const int tl = lane;
             const bool active = tl < kT;
             const int tls = active ? tl : 0;
             const uint32_t red_leader = mapa_u32(red, 0);
@@ -322,15 +336,158 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
 #pragma unroll
                     for (int t = 0; t < kBlk; t += 2) st_cluster_v2(dst + t * (uint32_t)sizeof(double), s[t], s[t + 1]);
                 }
-                fence_cluster();
+                // release.cluster arrive below is cumulative over the stores ordered before it by __syncwarp
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(sred_leader[gb & 1]);
             }
         }
-    } else if (special_idx < Cfg::kChainWarps) {
-        // ------------------------------------------------------------------ chain warps (one lane per trait; leader CTA)
-        const int cw = special_idx;
-        const int tl = cw * 32 + lane;
+    } else if (special_idx == 2) {
+        // ------------------------------------------------------------------ helper warp (leader CTA, sweep mode)
+        // Everything of a block that is NOT the serial recurrence: before the chain needs it, the split-K partials
+        // of S are summed (in place, into the ws = 0 rows) and the block's inputs beta_old and c (D + cst) are
+        // fetched from the p x q arrays into shared memory; after the chain, gam / mu go back to HBM and the
+        // per-trait running sums are accumulated.  With <= 16 traits per tile the two half-warps split the work.
+        if (P.mode == 0 && rank == 0) {
+            constexpr int kH = (kT <= 16) ? 2 : 1;
+            constexpr int kTP = kBlk / kH;           // SNP slots per lane
+            constexpr int kW0 = (WS + kH - 1) / kH;  // split-K partials per lane
+            const int half = (kH == 2) ? (lane >> 4) : 0;
+            const int tl = (kH == 2) ? (lane & 15) : lane;
+            const bool active = tl < kT;
+            const int tls = active ? tl : 0;
+            const int t0 = half * kTP;
+            int idn[kTP], idc[kTP];
+            long gb = 0;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                const int tile = group + ti * ngroups;
+                const int k = tile * kT + tls;
+                const bool valid = active && k < P.q;
+                const double sig2 = P.sig2_beta[k];
+                const double cst = -(P.log_tau[k] + P.log_sig2_inv + log(sig2)) / 2;  // src/coreLoop.cpp:56
+                double sg = 0.0, sgm2 = 0.0, sb2 = 0.0, sz = 0.0;
+                auto pre = [&](long g) {
+                    const int stage = (int)(g % kStages);
+                    mbar_wait(&full[stage], (uint32_t)((g / kStages) & 1));
+                    const int* ids = reinterpret_cast<const int*>(tiles + stage * Cfg::kTileDoubles + kBlk * XS + 128);
+                    double go[kTP], mo[kTP], dd[kTP];
+#pragma unroll
+                    for (int i = 0; i < kTP; ++i) {
+                        const int idt = ids[t0 + i];
+                        idn[i] = idt;
+                        const size_t off = (size_t)(idt < 0 ? 0 : idt) * P.q_pad + k;
+                        go[i] = P.gam[off];
+                        mo[i] = P.mu[off];
+                        dd[i] = P.dtab[off];
+                    }
+                    mbar_wait(&sdone[g & 1], (uint32_t)((g >> 1) & 1));
+                    double* sp0 = spart + (size_t)(g & 1) * WS * kT * Cfg::kSps + tls * Cfg::kSps;
+                    double s[kBlk];
+#pragma unroll
+                    for (int t = 0; t < kBlk; ++t) s[t] = 0.0;
+#pragma unroll
+                    for (int w2 = 0; w2 < kW0; ++w2) {
+                        const int w = half * kW0 + w2;
+                        if (kH == 1 || w < WS) {
+#pragma unroll
+                            for (int t = 0; t < kBlk; t += 2) {
+                                const double2 v = *reinterpret_cast<const double2*>(sp0 + w * kT * Cfg::kSps + t);
+                                s[t] += v.x;
+                                s[t + 1] += v.y;
+                            }
+                        }
+                    }
+                    if (kCl && ncta > 1) {  // + the other sample slices, already reduced by their CTAs
+                        mbar_wait_cluster(&sred[g & 1], (uint32_t)((g >> 1) & 1));
+                        if (half == 0) {
+                            for (int r2 = 1; r2 < ncta; ++r2) {
+                                const double* rp = red + ((size_t)((g & 1) * (kMaxCluster - 1) + (r2 - 1)) * kT + tls) * Cfg::kSps;
+#pragma unroll
+                                for (int t = 0; t < kBlk; t += 2) {
+                                    const double2 v = *reinterpret_cast<const double2*>(rp + t);
+                                    s[t] += v.x;
+                                    s[t + 1] += v.y;
+                                }
+                            }
+                        }
+                    }
+                    if (kH == 2) {
+#pragma unroll
+                        for (int t = 0; t < kBlk; ++t) s[t] += __shfl_xor_sync(0xffffffffu, s[t], 16);
+                    }
+                    if (half == 0 && active) {
+#pragma unroll
+                        for (int t = 0; t < kBlk; t += 2) {
+                            double2 v;
+                            v.x = s[t];
+                            v.y = s[t + 1];
+                            *reinterpret_cast<double2*>(sp0 + t) = v;
+                        }
+                    }
+                    double* io = iobuf + (size_t)(g & 1) * kBlk * 2 * kT;
+                    if (active) {
+#pragma unroll
+                        for (int i = 0; i < kTP; ++i) {
+                            const int t = t0 + i;
+                            io[(t * 2 + 0) * kT + tl] = idn[i] >= 0 ? go[i] * mo[i] : 0.0;  // beta_old (0 for padding slots)
+                            io[(t * 2 + 1) * kT + tl] = P.c * (dd[i] + cst);                // :75-77 without the mu^2 term
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&inready[g & 1]);
+                };
+                auto post = [&](long g) {
+                    double ww[kTP], ii[kTP];
+#pragma unroll
+                    for (int i = 0; i < kTP; ++i) {
+                        const size_t off = (size_t)(idc[i] < 0 ? 0 : idc[i]) * P.q_pad + k;
+                        ww[i] = P.wtab[off];
+                        ii[i] = P.i0tab[off];
+                    }
+                    mbar_wait(&dready[g & 1], (uint32_t)((g >> 1) & 1));
+                    const double* io = iobuf + (size_t)(g & 1) * kBlk * 2 * kT;
+#pragma unroll
+                    for (int i = 0; i < kTP; ++i) {
+                        const int t = t0 + i;
+                        const double gm = io[(t * 2 + 0) * kT + tls];
+                        const double m = io[(t * 2 + 1) * kT + tls];
+                        if (idc[i] >= 0) {
+                            const double bn = gm * m;  // :79
+                            sg += gm;
+                            sgm2 = fma(bn, m, sgm2);
+                            sb2 = fma(bn, bn, sb2);
+                            sz += fma(gm, ww[i], ii[i]);
+                            if (valid) {
+                                const size_t off = (size_t)idc[i] * P.q_pad + k;
+                                P.gam[off] = gm;
+                                P.mu[off] = m;
+                            }
+                        }
+                    }
+                };
+                pre(gb);
+                for (int b = 0; b < nb; ++b, ++gb) {
+#pragma unroll
+                    for (int i = 0; i < kTP; ++i) idc[i] = idn[i];
+                    if (b + 1 < nb) pre(gb + 1);
+                    post(gb);
+                }
+                if (kH == 2) {
+                    sg += __shfl_xor_sync(0xffffffffu, sg, 16);
+                    sgm2 += __shfl_xor_sync(0xffffffffu, sgm2, 16);
+                    sb2 += __shfl_xor_sync(0xffffffffu, sb2, 16);
+                    sz += __shfl_xor_sync(0xffffffffu, sz, 16);
+                }
+                if (valid && half == 0) {
+                    P.cs_gam[k] = sg;
+                    P.cs_gmu2[k] = sgm2;
+                    P.cs_b2[k] = sb2;
+                    P.cs_z[k] = sz;
+                }
+            }
+        }
+    } else if (special_idx == 0) {
+        // ------------------------------------------------------------------ chain warp (one lane per trait; leader CTA)
+        const int tl = lane;
         const bool active = tl < kT;
         const int tls = active ? tl : 0;  // inactive lanes shadow trait 0 without side effects
         uint32_t dbuf_remote[kMaxCluster], dready_remote[kMaxCluster][2];
@@ -341,156 +498,126 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 dready_remote[r2][1] = mapa_u32(&dready[1], r2);
             }
         }
+        // -Delta leaves for the MMA warps of every CTA of the cluster
+        auto publish = [&](long gb, const double (&nd)[kBlk]) {
+            double* drow = dbuf + (size_t)(gb & 1) * kT * kBlk + tls * kBlk;
+            if (active) {
+#pragma unroll
+                for (int t = 0; t < kBlk; t += 2) {
+                    double2 v;
+                    v.x = nd[t];
+                    v.y = nd[t + 1];
+                    *reinterpret_cast<double2*>(drow + t) = v;
+                    if (kCl)
+                        for (int r2 = 1; r2 < ncta; ++r2)
+                            st_cluster_v2(dbuf_remote[r2] + (uint32_t)(((size_t)(gb & 1) * kT * kBlk + tl * kBlk + t) * sizeof(double)), v.x, v.y);
+                }
+            }
+            // (no cluster fence: __syncwarp orders the lanes' stores before lane 0's release.cluster arrive, which is cumulative)
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&dready[gb & 1]);
+                if (kCl)
+                    for (int r2 = 1; r2 < ncta; ++r2) mbar_arrive_cluster(dready_remote[r2][gb & 1]);
+            }
+        };
         long gb = 0;
         for (int ti = 0; ti < my_tiles; ++ti) {
             const int tile = group + ti * ngroups;
             const int k = tile * kT + tls;
             const bool valid = active && k < P.q;
-            const double sig2 = P.sig2_beta[k], tauk = P.tau[k];
-            const double a = P.c * sig2 * tauk;                                   // src/coreLoop.cpp:73
-            const double hinv = 1.0 / (2.0 * sig2);                               // :76
-            const double cst = -(P.log_tau[k] + P.log_sig2_inv + log(sig2)) / 2;  // :56
-            double sg = 0.0, sgm2 = 0.0, sb2 = 0.0, sz = 0.0;
-            for (int b = 0; b < nb; ++b, ++gb) {
-                const int stage = (int)(gb % kStages);
-                mbar_wait(&full[stage], (uint32_t)((gb / kStages) & 1));
-                const double* xt = tiles + stage * Cfg::kTileDoubles;
-                const double* gband = xt + kBlk * XS;
-                const int* ids = reinterpret_cast<const int*>(gband + 128);
-                // all 40 loads are issued back to back (no use in between), so one DRAM/L2 round trip covers the block
-                double go[kBlk], mo[kBlk], dd[kBlk], ww[kBlk], ii[kBlk];
+            if (P.mode == 0) {
+                // ---- sweep: only the serial recurrence lives here; inputs arrive through shared memory (helper warp)
+                const double sig2 = P.sig2_beta[k];
+                const double a = P.c * sig2 * P.tau[k];             // src/coreLoop.cpp:73:  mu = a * s
+                const double bq = P.c * a * a / (2.0 * sig2);       // :76  c * mu^2 / (2 sig2_beta) = bq * s^2
+                double corr[kBlk];  // look-ahead correction of the NEXT block, accumulated while this one is resolved
 #pragma unroll
-                for (int t = 0; t < kBlk; ++t) {
-                    const int idt = ids[t];
-                    const size_t off = (size_t)(idt < 0 ? 0 : idt) * P.q_pad + k;
-                    go[t] = P.gam[off];
-                    mo[t] = P.mu[off];
-                    if (P.mode == 0) {
-                        dd[t] = P.dtab[off];
-                        ww[t] = P.wtab[off];
-                        ii[t] = P.i0tab[off];
-                    } else {
-                        dd[t] = ww[t] = ii[t] = 0.0;
-                    }
-                }
-                // the previous block's -Delta row is read back from shared memory for the look-ahead correction
-                double* drow = dbuf + (size_t)(gb & 1) * kT * kBlk + tls * kBlk;
-                const double* dprow = dbuf + (size_t)((gb + 1) & 1) * kT * kBlk + tls * kBlk;
-                double s[kBlk], nd[kBlk];
-                if (P.mode == 0) {
-                    mbar_wait(&sdone[gb & 1], (uint32_t)((gb >> 1) & 1));
-                    const double* sp = spart + (size_t)(gb & 1) * WS * kT * Cfg::kSps + tls * Cfg::kSps;
+                for (int t = 0; t < kBlk; ++t) corr[t] = 0.0;
+                for (int b = 0; b < nb; ++b, ++gb) {
+#ifdef AQ_TIMING
+                    long long tlast = clock64();
+#endif
+                    const int stage = (int)(gb % kStages);
+                    mbar_wait(&full[stage], (uint32_t)((gb / kStages) & 1));
+                    const double* gband = tiles + stage * Cfg::kTileDoubles + kBlk * XS;
+                    mbar_wait(&inready[gb & 1], (uint32_t)((gb >> 1) & 1));
+                    AQ_T(0);
+                    const double* sp0 = spart + (size_t)(gb & 1) * WS * kT * Cfg::kSps + tls * Cfg::kSps;
+                    double* io = iobuf + (size_t)(gb & 1) * kBlk * 2 * kT;
+                    double s[kBlk], bo[kBlk], ap[kBlk], nd[kBlk];
 #pragma unroll
-                    for (int t = 0; t < kBlk; ++t) s[t] = 0.0;
-#pragma unroll
-                    for (int w2 = 0; w2 < WS; ++w2) {
-#pragma unroll
-                        for (int t = 0; t < kBlk; t += 2) {
-                            const double2 v = *reinterpret_cast<const double2*>(sp + w2 * kT * Cfg::kSps + t);
-                            s[t] += v.x;
-                            s[t + 1] += v.y;
-                        }
-                    }
-                    if (kCl && ncta > 1) {  // + the other sample slices, already reduced by their CTAs
-                        mbar_wait_cluster(&sred[gb & 1], (uint32_t)((gb >> 1) & 1));
-                        for (int r2 = 1; r2 < ncta; ++r2) {
-                            const double* rp = red + ((size_t)((gb & 1) * (kMaxCluster - 1) + (r2 - 1)) * kT + tls) * Cfg::kSps;
-#pragma unroll
-                            for (int t = 0; t < kBlk; t += 2) {
-                                const double2 v = *reinterpret_cast<const double2*>(rp + t);
-                                s[t] += v.x;
-                                s[t + 1] += v.y;
-                            }
-                        }
-                    }
-                    // look-ahead correction: S was formed before the previous block's update was applied
-                    if (b > 0) {
-#pragma unroll
-                        for (int u = 0; u < kBlk; u += 2) {
-                            const double2 nd2 = *reinterpret_cast<const double2*>(dprow + u);  // -Delta_prev[u], [u+1]
-#pragma unroll
-                            for (int t = 0; t < kBlk; ++t) {
-                                s[t] = fma(gband[t * 16 + u], nd2.x, s[t]);
-                                s[t] = fma(gband[t * 16 + u + 1], nd2.y, s[t]);
-                            }
-                        }
-                    }
-                    double sum_i0 = 0.0;
-#pragma unroll
-                    for (int t = 0; t < kBlk; ++t) {
-                        const bool live = ids[t] >= 0;
-                        go[t] = live ? go[t] * mo[t] : 0.0;  // beta_old (0 for padding slots: their X column is 0)
-                        s[t] = fma(go[t], gband[t * 16 + 8 + t], s[t]);  // leave-one-out: + beta_old |X_t|^2
-                        sum_i0 += live ? ii[t] : 0.0;
+                    for (int t = 0; t < kBlk; t += 2) {
+                        const double2 v = *reinterpret_cast<const double2*>(sp0 + t);
+                        s[t] = v.x;
+                        s[t + 1] = v.y;
                     }
 #pragma unroll
                     for (int t = 0; t < kBlk; ++t) {
-                        const double m = a * s[t];                                    // :73
-                        const double x = P.c * (dd[t] - m * m * hinv + cst);          // :75-77
-                        const double gm = logistic_neg(x);                            // 1/(1+e^x) == exp(-log1pexp(x))
-                        const double bn = gm * m;                                     // :79
-                        const double dlt = bn - go[t];                                // 0 for padding slots (m == 0)
+                        bo[t] = io[(t * 2 + 0) * kT + tls];
+                        ap[t] = io[(t * 2 + 1) * kT + tls];
+                    }
 #pragma unroll
-                        for (int u = t + 1; u < kBlk; ++u) s[u] = fma(-gband[u * 16 + 8 + t], dlt, s[u]);
+                    for (int t = 0; t < kBlk; ++t) {
+                        // S was formed before the previous block's update was applied (corr); leave-one-out: + beta_old |X_t|^2
+                        s[t] = fma(bo[t], gband[t * 16 + 8 + t], s[t] + corr[t]);
+                        corr[t] = 0.0;
+                    }
+                    AQ_T(1);
+#pragma unroll
+                    for (int t = 0; t < kBlk; ++t) {
+                        const double st = s[t];
+                        const double m = a * st;                             // :73
+                        const double x = fma(st * st, -bq, ap[t]);           // :75-77
+                        const double gm = logistic_neg(x);                   // 1/(1+e^x) == exp(-log1pexp(x))
+                        const double dlt = fma(gm, m, -bo[t]);               // :79 beta_new - beta_old (0 for padding slots)
+                        const double* grow = gband + t * 16;                 // row t: [next block | this block]
+#pragma unroll
+                        for (int u = t + 1; u < kBlk; ++u) s[u] = fma(-grow[8 + u], dlt, s[u]);
+#pragma unroll
+                        for (int u = 0; u < kBlk; ++u) corr[u] = fma(-grow[u], dlt, corr[u]);
                         nd[t] = -dlt;
-                        const int idt = ids[t];
-                        if (idt >= 0) {
-                            sg += gm;
-                            sgm2 = fma(gm * m, m, sgm2);
-                            sb2 = fma(bn, bn, sb2);
-                            sz = fma(gm, ww[t], sz);
-                            if (valid) {
-                                const size_t off = (size_t)idt * P.q_pad + k;
-                                P.gam[off] = gm;
-                                P.mu[off] = m;
-                            }
+                        if (active) {
+                            io[(t * 2 + 0) * kT + tl] = gm;
+                            io[(t * 2 + 1) * kT + tl] = m;
                         }
                     }
-                    sz += sum_i0;
-                } else {
-                    if (gb >= 2) {  // -Delta buffer (gb & 1) free again in every CTA
-                        if (kCl) mbar_wait_cluster(&dcons[gb & 1], (uint32_t)(((gb >> 1) - 1) & 1));
-                        else mbar_wait(&dcons[gb & 1], (uint32_t)(((gb >> 1) - 1) & 1));
-                    }
+                    AQ_T(2);
+                    publish(gb, nd);
+                    AQ_T(3);
+                }
+            } else {
+                // ---- mode 1: R = Y - X beta from the loaded state, and its per-trait sums
+                double sg = 0.0, sgm2 = 0.0, sb2 = 0.0;
+                for (int b = 0; b < nb; ++b, ++gb) {
+                    const int stage = (int)(gb % kStages);
+                    mbar_wait(&full[stage], (uint32_t)((gb / kStages) & 1));
+                    const int* ids = reinterpret_cast<const int*>(tiles + stage * Cfg::kTileDoubles + kBlk * XS + 128);
+                    double nd[kBlk];
 #pragma unroll
                     for (int t = 0; t < kBlk; ++t) {
-                        const bool live = ids[t] >= 0;
-                        const double bo = live ? go[t] * mo[t] : 0.0;  // R = Y - X beta: subtract X_t beta_t
-                        if (live) {
-                            sg += go[t];
-                            sgm2 = fma(go[t] * mo[t], mo[t], sgm2);
+                        const int idt = ids[t];
+                        const size_t off = (size_t)(idt < 0 ? 0 : idt) * P.q_pad + k;
+                        const double go = P.gam[off], mo = P.mu[off];
+                        const double bo = idt >= 0 ? go * mo : 0.0;
+                        if (idt >= 0) {
+                            sg += go;
+                            sgm2 = fma(bo, mo, sgm2);
                             sb2 = fma(bo, bo, sb2);
                         }
                         nd[t] = -bo;
                     }
-                }
-                // publish -Delta only now: a shared-memory store inside the step loop would order every later Gram-band
-                // load behind it (possible aliasing) and put the LDS latency on the serial path of each step
-                if (active) {
-#pragma unroll
-                    for (int t = 0; t < kBlk; t += 2) {
-                        double2 v;
-                        v.x = nd[t];
-                        v.y = nd[t + 1];
-                        *reinterpret_cast<double2*>(drow + t) = v;
-                        if (kCl)
-                            for (int r2 = 1; r2 < ncta; ++r2)
-                                st_cluster_v2(dbuf_remote[r2] + (uint32_t)(((size_t)(gb & 1) * kT * kBlk + tl * kBlk + t) * sizeof(double)), v.x, v.y);
+                    if (gb >= 2) {  // -Delta buffer (gb & 1) free again in every CTA
+                        if (kCl) mbar_wait_cluster(&dcons[gb & 1], (uint32_t)(((gb >> 1) - 1) & 1));
+                        else mbar_wait(&dcons[gb & 1], (uint32_t)(((gb >> 1) - 1) & 1));
                     }
+                    publish(gb, nd);
                 }
-                if (kCl) fence_cluster();
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&dready[gb & 1]);
-                    if (kCl)
-                        for (int r2 = 1; r2 < ncta; ++r2) mbar_arrive_cluster(dready_remote[r2][gb & 1]);
+                if (valid) {
+                    P.cs_gam[k] = sg;
+                    P.cs_gmu2[k] = sgm2;
+                    P.cs_b2[k] = sb2;
                 }
-            }
-            if (valid) {
-                P.cs_gam[k] = sg;
-                P.cs_gmu2[k] = sgm2;
-                P.cs_b2[k] = sb2;
-                if (P.mode == 0) P.cs_z[k] = sz;
             }
         }
     }
