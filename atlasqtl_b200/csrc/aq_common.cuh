@@ -100,6 +100,13 @@ __device__ __forceinline__ void st_cluster_v2(uint32_t raddr, double a, double b
 __device__ __forceinline__ void st_cluster_f64(uint32_t raddr, double a) {
     asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(raddr), "d"(a) : "memory");
 }
+// asynchronous 16-byte store into another CTA's shared memory; its bytes are accounted (complete_tx) on that CTA's
+// mbarrier `rbar`, so the receiver needs no remote arrive and the sender no fence
+__device__ __forceinline__ void st_async_v2(uint32_t raddr, double a, double b, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(raddr), "d"(a),
+                 "d"(b), "r"(rbar)
+                 : "memory");
+}
 __device__ __forceinline__ void fence_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t raddr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");

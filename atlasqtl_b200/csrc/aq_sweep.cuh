@@ -26,9 +26,13 @@
 #pragma once
 #include "aq_common.cuh"
 #ifdef AQ_TIMING
-#define AQ_T(i) do { long long t_ = clock64(); if (blockIdx.x == 0 && lane == 0 && special_idx == 0 && P.timing) P.timing[i] += t_ - tlast; tlast = t_; } while (0)
+// development only: per-section cycle sums of the chain (0-3) and helper (4-9) warps of CTA 0, kept in registers and
+// written once at the end (a global read-modify-write per probe would put an L2 round trip into every section)
+#define AQ_T(i) do { long long t_ = clock64(); tacc[i] += t_ - tlast; tlast = t_; } while (0)
+#define AQ_T0() long long tlast = clock64()
 #else
 #define AQ_T(i) do { } while (0)
+#define AQ_T0() do { } while (0)
 #endif
 
 namespace aq {
@@ -84,6 +88,7 @@ struct SweepCfg {
     static constexpr size_t kDbufDoubles = (size_t)2 * kT * kBlk;
     static constexpr size_t kRsqDoubles = (size_t)WS * kT;
     static constexpr size_t kIoDoubles = (size_t)2 * kBlk * 2 * kT;  // [2][kBlk][2][kT]: in beta_old, c (D + cst); out gam, mu
+    static constexpr uint32_t kDeltaBytes = (uint32_t)(kT * kBlk * sizeof(double));  // one -Delta block
     // cluster variant only: followers' reduced S tiles and squared-norm partials land in the leader's shared memory
     static constexpr size_t kRedDoubles = kCl ? (size_t)2 * (kMaxCluster - 1) * kT * kSps : 0;
     static constexpr size_t kRsqAllDoubles = kCl ? (size_t)(kMaxCluster - 1) * kT : 0;
@@ -123,6 +128,9 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
     uint64_t* inready = bars + 2 * kStages + 9;  // [2]  helper warp staged S and the block's inputs for the chain
 
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef AQ_TIMING
+    long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#endif
     // role map: SMSP 3 (wid % 4 == 3) hosts the special warps, SMSPs 0-2 the MMA warps
     const bool is_special = (wid & 3) == 3;
     const int mma_idx = wid - (wid >> 2);   // 0..8 for MMA warps
@@ -137,7 +145,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
             mbar_init(&sdone[s], Cfg::kMmaWarps);
             mbar_init(&dready[s], Cfg::kChainWarps);
             mbar_init(&dcons[s], Cfg::kMmaWarps * ncta);
-            mbar_init(&sred[s], ncta > 1 ? ncta - 1 : 1);
+            mbar_init(&sred[s], 1);
             mbar_init(&inready[s], 1);
         }
         mbar_init(&rsqbar[0], ncta > 1 ? ncta - 1 : 1);
@@ -232,10 +240,22 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 // ---- rank-8 update with -Delta_b
                 const int stage = (int)(gb % kStages);
                 if (P.mode != 0) mbar_wait(&full[stage], (uint32_t)((gb / kStages) & 1));  // sweep mode: S phase waited
-                if (kCl) mbar_wait_cluster(&dready[gb & 1], (uint32_t)((gb >> 1) & 1));
-                else mbar_wait(&dready[gb & 1], (uint32_t)((gb >> 1) & 1));
+                // (followers: -Delta arrives by an async bulk copy accounted on this barrier, so a CTA-scope wait is enough;
+                // an acquire.cluster wait would invalidate L1 (CCTL.IVALL) on every block)
+                mbar_wait(&dready[gb & 1], (uint32_t)((gb >> 1) & 1));
                 const double* xt = tiles + stage * Cfg::kTileDoubles;
                 const double* db = dbuf + (size_t)(gb & 1) * kT * kBlk;
+                if (kCl && rank == 0) {
+                    // leader: forward the kT x 8 block of -Delta to every follower, one 16-byte asynchronous DSMEM store per
+                    // lane, accounted on the follower's barrier (armed by its reducer warp)
+                    constexpr int kV2 = kT * kBlk / 2;
+                    const int nsend = (ncta - 1) * kV2;
+                    for (int L = mtid; L < nsend; L += Cfg::kMmaWarps * 32) {
+                        const int r2 = 1 + L / kV2, idx = L % kV2;
+                        const double2 v = *reinterpret_cast<const double2*>(db + 2 * idx);
+                        st_async_v2(mapa_u32(db + 2 * idx, r2), v.x, v.y, mapa_u32(&dready[gb & 1], r2));
+                    }
+                }
                 double nd[MT][2];
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
@@ -307,38 +327,53 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
         }
     } else if (special_idx == 0 && rank != 0) {
         // ------------------------------------------------------------------ follower CTA: S-tile reducer warp
-        // Sums this CTA's WS split-K partials and ships the kT x 8 tile into the leader's shared memory.
-        if (P.mode == 0) {
-            const int tl = lane;
-            const bool active = tl < kT;
-            const int tls = active ? tl : 0;
-            const uint32_t red_leader = mapa_u32(red, 0);
-            const uint32_t sred_leader[2] = {mapa_u32(&sred[0], 0), mapa_u32(&sred[1], 0)};
-            const long total = (long)my_tiles * nb;
-            for (long gb = 0; gb < total; ++gb) {
-                mbar_wait(&sdone[gb & 1], (uint32_t)((gb >> 1) & 1));
-                const double* sp = spart + (size_t)(gb & 1) * WS * kT * Cfg::kSps + tls * Cfg::kSps;
-                double s[kBlk];
+        // Arms this CTA's -Delta barrier for every block (the leader's asynchronous stores complete it) and, in sweep
+        // mode, sums this CTA's WS split-K partials and ships the kT x 8 tile into the leader's shared memory with
+        // st.async (fire-and-forget DSMEM stores whose bytes are accounted on the leader's barrier: no remote arrive,
+        // no fence).  With <= 16 traits per tile the two half-warps split the work.
+        constexpr int kH = (kT <= 16) ? 2 : 1;
+        constexpr int kTP = kBlk / kH;
+        constexpr int kW0 = (WS + kH - 1) / kH;
+        const int half = (kH == 2) ? (lane >> 4) : 0;
+        const int tl = (kH == 2) ? (lane & 15) : lane;
+        const bool active = tl < kT;
+        const int tls = active ? tl : 0;
+        const uint32_t red_leader = mapa_u32(red, 0);
+        const uint32_t sred_leader[2] = {mapa_u32(&sred[0], 0), mapa_u32(&sred[1], 0)};
+        const long total = (long)my_tiles * nb;
+        for (long gb = 0; gb < total; ++gb) {
+            if (gb >= 2) mbar_wait(&dready[gb & 1], (uint32_t)(((gb >> 1) - 1) & 1));  // the phase of block gb - 2 is over
+            if (lane == 0) mbar_arrive_expect_tx(&dready[gb & 1], Cfg::kDeltaBytes);
+            if (P.mode != 0) continue;
+            mbar_wait(&sdone[gb & 1], (uint32_t)((gb >> 1) & 1));
+            const double* sp = spart + (size_t)(gb & 1) * WS * kT * Cfg::kSps + tls * Cfg::kSps;
+            double s[kBlk];
 #pragma unroll
-                for (int t = 0; t < kBlk; ++t) s[t] = 0.0;
+            for (int t = 0; t < kBlk; ++t) s[t] = 0.0;
 #pragma unroll
-                for (int w2 = 0; w2 < WS; ++w2) {
+            for (int w2 = 0; w2 < kW0; ++w2) {
+                const int w = half * kW0 + w2;
+                if (kH == 1 || w < WS) {
 #pragma unroll
                     for (int t = 0; t < kBlk; t += 2) {
-                        const double2 v = *reinterpret_cast<const double2*>(sp + w2 * kT * Cfg::kSps + t);
+                        const double2 v = *reinterpret_cast<const double2*>(sp + w * kT * Cfg::kSps + t);
                         s[t] += v.x;
                         s[t + 1] += v.y;
                     }
                 }
-                if (active) {
-                    const uint32_t dst = red_leader + (uint32_t)(((((gb & 1) * (kMaxCluster - 1)) + (rank - 1)) * kT + tl) *
-                                                                 Cfg::kSps * sizeof(double));
+            }
+            if (kH == 2) {
 #pragma unroll
-                    for (int t = 0; t < kBlk; t += 2) st_cluster_v2(dst + t * (uint32_t)sizeof(double), s[t], s[t + 1]);
+                for (int t = 0; t < kBlk; ++t) s[t] += __shfl_xor_sync(0xffffffffu, s[t], 16);
+            }
+            if (active) {
+                const uint32_t dst = red_leader + (uint32_t)(((((gb & 1) * (kMaxCluster - 1)) + (rank - 1)) * kT + tl) *
+                                                             Cfg::kSps * sizeof(double));
+#pragma unroll
+                for (int i = 0; i < kTP; i += 2) {
+                    const int t = half * kTP + i;
+                    st_async_v2(dst + t * (uint32_t)sizeof(double), s[t], s[t + 1], sred_leader[gb & 1]);
                 }
-                // release.cluster arrive below is cumulative over the stores ordered before it by __syncwarp
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(sred_leader[gb & 1]);
             }
         }
     } else if (special_idx == 2) {
@@ -366,6 +401,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 const double cst = -(P.log_tau[k] + P.log_sig2_inv + log(sig2)) / 2;  // src/coreLoop.cpp:56
                 double sg = 0.0, sgm2 = 0.0, sb2 = 0.0, sz = 0.0;
                 auto pre = [&](long g) {
+                    AQ_T0();
                     const int stage = (int)(g % kStages);
                     mbar_wait(&full[stage], (uint32_t)((g / kStages) & 1));
                     const int* ids = reinterpret_cast<const int*>(tiles + stage * Cfg::kTileDoubles + kBlk * XS + 128);
@@ -380,6 +416,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                         dd[i] = P.dtab[off];
                     }
                     mbar_wait(&sdone[g & 1], (uint32_t)((g >> 1) & 1));
+                    AQ_T(4);
                     double* sp0 = spart + (size_t)(g & 1) * WS * kT * Cfg::kSps + tls * Cfg::kSps;
                     double s[kBlk];
 #pragma unroll
@@ -396,8 +433,11 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                             }
                         }
                     }
-                    if (kCl && ncta > 1) {  // + the other sample slices, already reduced by their CTAs
-                        mbar_wait_cluster(&sred[g & 1], (uint32_t)((g >> 1) & 1));
+                    if (kCl && ncta > 1) {  // + the other sample slices, already reduced (and stored here) by their CTAs
+                        if (lane == 0) mbar_arrive_expect_tx(&sred[g & 1], (uint32_t)(ncta - 1) * Cfg::kDeltaBytes);
+                        AQ_T(5);
+                        mbar_wait(&sred[g & 1], (uint32_t)((g >> 1) & 1));
+                        AQ_T(6);
                         if (half == 0) {
                             for (int r2 = 1; r2 < ncta; ++r2) {
                                 const double* rp = red + ((size_t)((g & 1) * (kMaxCluster - 1) + (r2 - 1)) * kT + tls) * Cfg::kSps;
@@ -434,6 +474,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&inready[g & 1]);
+                    AQ_T(7);
                 };
                 auto post = [&](long g) {
                     double ww[kTP], ii[kTP];
@@ -443,7 +484,9 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                         ww[i] = P.wtab[off];
                         ii[i] = P.i0tab[off];
                     }
+                    AQ_T0();
                     mbar_wait(&dready[g & 1], (uint32_t)((g >> 1) & 1));
+                    AQ_T(8);
                     const double* io = iobuf + (size_t)(g & 1) * kBlk * 2 * kT;
 #pragma unroll
                     for (int i = 0; i < kTP; ++i) {
@@ -463,6 +506,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                             }
                         }
                     }
+                    AQ_T(9);
                 };
                 pre(gb);
                 for (int b = 0; b < nb; ++b, ++gb) {
@@ -490,36 +534,21 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
         const int tl = lane;
         const bool active = tl < kT;
         const int tls = active ? tl : 0;  // inactive lanes shadow trait 0 without side effects
-        uint32_t dbuf_remote[kMaxCluster], dready_remote[kMaxCluster][2];
-        if (kCl) {
-            for (int r2 = 1; r2 < ncta; ++r2) {
-                dbuf_remote[r2] = mapa_u32(dbuf, r2);
-                dready_remote[r2][0] = mapa_u32(&dready[0], r2);
-                dready_remote[r2][1] = mapa_u32(&dready[1], r2);
-            }
-        }
-        // -Delta leaves for the MMA warps of every CTA of the cluster
+        // -Delta leaves for this CTA's MMA warps (which forward it to the other CTAs of a cluster): this warp never issues
+        // a remote operation, they would sit in its load/store queue on the serial path
         auto publish = [&](long gb, const double (&nd)[kBlk]) {
-            double* drow = dbuf + (size_t)(gb & 1) * kT * kBlk + tls * kBlk;
+            double* dblk = dbuf + (size_t)(gb & 1) * kT * kBlk;
             if (active) {
 #pragma unroll
                 for (int t = 0; t < kBlk; t += 2) {
                     double2 v;
                     v.x = nd[t];
                     v.y = nd[t + 1];
-                    *reinterpret_cast<double2*>(drow + t) = v;
-                    if (kCl)
-                        for (int r2 = 1; r2 < ncta; ++r2)
-                            st_cluster_v2(dbuf_remote[r2] + (uint32_t)(((size_t)(gb & 1) * kT * kBlk + tl * kBlk + t) * sizeof(double)), v.x, v.y);
+                    *reinterpret_cast<double2*>(dblk + tl * kBlk + t) = v;
                 }
             }
-            // (no cluster fence: __syncwarp orders the lanes' stores before lane 0's release.cluster arrive, which is cumulative)
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&dready[gb & 1]);
-                if (kCl)
-                    for (int r2 = 1; r2 < ncta; ++r2) mbar_arrive_cluster(dready_remote[r2][gb & 1]);
-            }
+            if (lane == 0) mbar_arrive(&dready[gb & 1]);
         };
         long gb = 0;
         for (int ti = 0; ti < my_tiles; ++ti) {
@@ -535,9 +564,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
 #pragma unroll
                 for (int t = 0; t < kBlk; ++t) corr[t] = 0.0;
                 for (int b = 0; b < nb; ++b, ++gb) {
-#ifdef AQ_TIMING
-                    long long tlast = clock64();
-#endif
+                    AQ_T0();
                     const int stage = (int)(gb % kStages);
                     mbar_wait(&full[stage], (uint32_t)((gb / kStages) & 1));
                     const double* gband = tiles + stage * Cfg::kTileDoubles + kBlk * XS;
@@ -621,6 +648,11 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
             }
         }
     }
+#ifdef AQ_TIMING
+    if (blockIdx.x == 0 && lane == 0 && P.timing && is_special)
+        for (int i = 0; i < 10; ++i)
+            if (tacc[i]) atomicAdd(reinterpret_cast<unsigned long long*>(P.timing) + i, (unsigned long long)tacc[i]);
+#endif
     if (kCl) {
         __syncwarp();
         cluster_sync_all();  // keep every CTA's shared memory alive until all remote stores / arrives have landed
