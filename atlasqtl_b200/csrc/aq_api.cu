@@ -35,22 +35,10 @@ int fail(int code, const std::string& msg) {
         }                                                                                               \
     } while (0)
 
-// ---- kernel configurations (SweepCfg<WS, WT, MT, NT, clustered>): picked by n at aq_create time.
-// 9 MMA warps split a CTA's samples (72 NT of them); each holds MT 8-trait tiles: MT * NT * 2 accumulator doubles.
-// n <= 1008: one CTA per trait tile.  n > 1008: a thread-block cluster of 2 / 4 / 8 CTAs splits the samples.
-using CfgN1008 = SweepCfg<9, 1, 2, 14>;  // n <= 1008, 16 traits / tile
-using CfgN720 = SweepCfg<9, 1, 3, 10>;   // n <= 720,  24 traits / tile
-using CfgN504 = SweepCfg<9, 1, 4, 7>;    // n <= 504,  32 traits / tile
-using CfgN360 = SweepCfg<9, 1, 4, 5>;    // n <= 360,  32 traits / tile (one chain lane per trait)
-using CfgN216 = SweepCfg<9, 1, 4, 3>;    // n <= 216,  32 traits / tile
-using CfgN144 = SweepCfg<9, 1, 4, 2>;    // n <= 144,  32 traits / tile
-using CfgC7 = SweepCfg<9, 1, 4, 7, true>;    // clustered: 504 samples per CTA, 32 traits / tile
-using CfgC8 = SweepCfg<9, 1, 3, 8, true>;    // 576, 24
-using CfgC9 = SweepCfg<9, 1, 3, 9, true>;    // 648, 24
-using CfgC10 = SweepCfg<9, 1, 2, 10, true>;  // 720, 16
-using CfgC11 = SweepCfg<9, 1, 2, 11, true>;  // 792, 16
-using CfgC12 = SweepCfg<9, 1, 2, 12, true>;  // 864, 16
-
+// ---- kernel configurations (SweepCfg<MT, NT, clustered>): picked by n at aq_create time.
+// 14 MMA warps split a CTA's samples (112 NT of them); each holds MT 8-trait tiles: MT * NT * 2 accumulator doubles
+// (<= 40: the 16-warp CTA leaves 128 registers per thread).  n <= 1008: one CTA per trait tile.  n > 1008: a
+// thread-block cluster of 2 / 4 / 8 CTAs splits the samples (up to n = 7168).
 struct CfgInfo {
     int id, n_pad, xs, kT, threads;   // n_pad: samples per CTA (slice), padded
     size_t smem, tile_doubles;
@@ -60,48 +48,36 @@ template <class C>
 CfgInfo info(int id, int ncta = 1) {
     return CfgInfo{id, C::kNPad, C::kXS, C::kT, C::kThreads, C::kSmemBytes, C::kTileDoubles, ncta};
 }
+constexpr int mt_of_nt(int nt) { return nt >= 8 ? 2 : (nt >= 6 ? 3 : 4); }  // traits / tile = 8 MT: 16, 24, 32
+constexpr int kMaxNT = 9;    // single CTA: n <= 1008
+constexpr int kMaxNTCl = 8;  // clustered (the leader also buffers the followers' S tiles): n <= ncta * 896
+template <int NT, bool CL>
+using CfgOf = SweepCfg<mt_of_nt(NT), NT, CL>;
+
+// id = nt (single CTA) or 100 + nt (clustered)
+template <int NT>
+bool pick_nt(int nt, bool cl, int ncta, CfgInfo* out) {
+    if (nt == NT) {
+        if (!cl) *out = info<CfgOf<NT, false>>(NT, 1);
+        else if constexpr (NT <= kMaxNTCl) *out = info<CfgOf<NT, true>>(100 + NT, ncta);
+        else return false;
+        return true;
+    }
+    if constexpr (NT < kMaxNT) return pick_nt<NT + 1>(nt, cl, ncta, out);
+    return false;
+}
 
 bool pick_cfg(int n, CfgInfo* out) {
     // development knob: AQ_FORCE_CLUSTER=2|4|8 selects the sample-split cluster kernel even where one CTA suffices
     const char* fc = std::getenv("AQ_FORCE_CLUSTER");
-    const int force = fc ? std::atoi(fc) : 0;
-    if (force == 2 || force == 4 || force == 8) {
-        int nt = (n + 72 * force - 1) / (72 * force);
-        if (nt < 7) nt = 7;
-        if (nt <= 12) {
-            switch (nt) {
-                case 7: *out = info<CfgC7>(107, force); break;
-                case 8: *out = info<CfgC8>(108, force); break;
-                case 9: *out = info<CfgC9>(109, force); break;
-                case 10: *out = info<CfgC10>(110, force); break;
-                case 11: *out = info<CfgC11>(111, force); break;
-                default: *out = info<CfgC12>(112, force); break;
-            }
-            return true;
-        }
-    }
-    if (n <= 144) *out = info<CfgN144>(5);
-    else if (n <= 216) *out = info<CfgN216>(4);
-    else if (n <= 360) *out = info<CfgN360>(3);
-    else if (n <= 504) *out = info<CfgN504>(2);
-    else if (n <= 720) *out = info<CfgN720>(1);
-    else if (n <= 1008) *out = info<CfgN1008>(0);
-    else {
-        int ncta = 2;
-        while (ncta <= kMaxCluster && n > ncta * 864) ncta *= 2;
+    int ncta = fc ? std::atoi(fc) : 0;
+    if (ncta != 2 && ncta != 4 && ncta != 8) ncta = 1;
+    while (n > ncta * 112 * (ncta > 1 ? kMaxNTCl : kMaxNT)) {
+        ncta *= 2;
         if (ncta > kMaxCluster) return false;
-        int nt = (n + 72 * ncta - 1) / (72 * ncta);
-        if (nt < 7) nt = 7;
-        switch (nt) {
-            case 7: *out = info<CfgC7>(107, ncta); break;
-            case 8: *out = info<CfgC8>(108, ncta); break;
-            case 9: *out = info<CfgC9>(109, ncta); break;
-            case 10: *out = info<CfgC10>(110, ncta); break;
-            case 11: *out = info<CfgC11>(111, ncta); break;
-            default: *out = info<CfgC12>(112, ncta); break;
-        }
     }
-    return true;
+    const int nt = (n + 112 * ncta - 1) / (112 * ncta);
+    return pick_nt<1>(nt, ncta > 1, ncta, out);
 }
 
 }  // namespace
@@ -123,7 +99,7 @@ struct aq_ctx {
     int stage_cols = 0;
     size_t n_partials = 0;
     int* order_dev = nullptr;
-    std::vector<int32_t> order;
+    std::vector<int32_t> order, order_pad;
     std::vector<double> hbuf;   // pinned-size-agnostic host scratch
     bool have_state = false, have_tables = false;
     int64_t launches = 0;
@@ -171,8 +147,18 @@ int launch_sweep_t(aq_ctx* c, const SweepParams& P) {
     return AQ_OK;
 }
 
+template <int NT>
+int launch_sweep_id(aq_ctx* c, const SweepParams& P) {
+    if (c->cfg.id == NT) return launch_sweep_t<CfgOf<NT, false>>(c, P);
+    if constexpr (NT <= kMaxNTCl)
+        if (c->cfg.id == 100 + NT) return launch_sweep_t<CfgOf<NT, true>>(c, P);
+    if constexpr (NT < kMaxNT) return launch_sweep_id<NT + 1>(c, P);
+    return fail(AQ_EUNSUPPORTED, "no kernel configuration");
+}
+
 int launch_sweep(aq_ctx* c, int mode, double cc, double log_sig2_inv) {
     SweepParams P;
+    P.order = c->order_dev;
     P.xtiles = c->xtiles;
     P.tile_stride = c->cfg.tile_doubles;
     P.nb = c->nb;
@@ -210,21 +196,8 @@ int launch_sweep(aq_ctx* c, int mode, double cc, double log_sig2_inv) {
         P.timing = tbuf;
     }
 #endif
-    switch (c->cfg.id) {
-        case 0: return launch_sweep_t<CfgN1008>(c, P);
-        case 1: return launch_sweep_t<CfgN720>(c, P);
-        case 2: return launch_sweep_t<CfgN504>(c, P);
-        case 3: return launch_sweep_t<CfgN360>(c, P);
-        case 4: return launch_sweep_t<CfgN216>(c, P);
-        case 5: return launch_sweep_t<CfgN144>(c, P);
-        case 107: return launch_sweep_t<CfgC7>(c, P);
-        case 108: return launch_sweep_t<CfgC8>(c, P);
-        case 109: return launch_sweep_t<CfgC9>(c, P);
-        case 110: return launch_sweep_t<CfgC10>(c, P);
-        case 111: return launch_sweep_t<CfgC11>(c, P);
-        case 112: return launch_sweep_t<CfgC12>(c, P);
-    }
-    return fail(AQ_EUNSUPPORTED, "no kernel configuration");
+    return launch_sweep_id<1>(c, P);
+
 }
 
 int upload_pxq(aq_ctx* c, const double* host, double* dev) {
@@ -270,7 +243,9 @@ int fetch_outputs(aq_ctx* c, double* o0, double* o1, double* o2, double* o3, dou
 }
 
 int retile(aq_ctx* c) {
-    AQ_CUDA(cudaMemcpyAsync(c->order_dev, c->order.data(), sizeof(int32_t) * c->p, cudaMemcpyHostToDevice, c->stream));
+    c->order_pad.assign(c->p_pad, -1);  // padding slots of the last block carry -1, as in the tile images
+    std::copy(c->order.begin(), c->order.end(), c->order_pad.begin());
+    AQ_CUDA(cudaMemcpyAsync(c->order_dev, c->order_pad.data(), sizeof(int32_t) * c->p_pad, cudaMemcpyHostToDevice, c->stream));
     build_tiles_kernel<<<dim3(c->nb, c->cfg.ncta), 256, 0, c->stream>>>(c->xraw, c->order_dev, c->n, c->p, c->cfg.xs,
                                                                          c->cfg.n_pad, c->cfg.tile_doubles, c->xtiles);
     AQ_CUDA(cudaGetLastError());
@@ -358,7 +333,7 @@ int aq_create(aq_ctx** out, int device, int n, int p, int q_local, const double*
     if (n < 2 || p < 1 || q_local < 1) return fail(AQ_EINVAL, "aq_create: need n >= 2, p >= 1, q >= 1");
     CfgInfo cfg;
     if (!pick_cfg(n, &cfg))
-        return fail(AQ_EUNSUPPORTED, "aq_create: n > 6912 is beyond the 8-CTA sample-split cluster kernel");
+        return fail(AQ_EUNSUPPORTED, "aq_create: n > 7168 is beyond the 8-CTA sample-split cluster kernel");
     int sm = 0;
     int rc = aq_device_info(device, &sm, nullptr, nullptr);
     if (rc != AQ_OK) return rc;

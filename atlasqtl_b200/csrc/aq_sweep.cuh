@@ -1,24 +1,24 @@
 // The CAVI Gauss-Seidel sweep kernel (sm_100a): coreDualLoop (reference src/coreLoop.cpp:38-86) in
 // sample space, blocked over SNPs, one persistent CTA per trait tile.
 //
-// Roles inside a CTA (warp-specialised, no __syncthreads in the steady state).  The fp64 tensor op
-// (DMMA) and scalar fp64 math share one pipe per SM sub-partition (SMSP = warp id % 4); a chain lane's
-// dependent DFMA/DADD sequence queued behind 16-cycle DMMAs runs ~2-3x slower (ncu: stall_math on the
-// chain warp, profiles/r1_ncu_sweep_c4_v1.txt).  So the 9 MMA warps live on SMSPs 0-2 (warp id % 4 != 3)
-// and the serial chain gets SMSP 3 to itself (warp ids 3, 7, 11):
-//   9 "MMA" warps   hold the tile's residual R^T (traits x samples) in REGISTERS as the accumulator
+// Roles inside a CTA of 16 warps (warp-specialised, no __syncthreads in the steady state).  The fp64 tensor op
+// (DMMA) and scalar fp64 math share one pipe per SM sub-partition (SMSP = warp id % 4); the serial chain is
+// latency bound and runs ~2-3x slower behind a saturated DMMA stream (ncu: stall_math on the chain warp,
+// profiles/r1_ncu_sweep_c4_v1_chain_shares_dmma_pipe.txt).  So SMSPs 0-2 carry four MMA warps each (pipe
+// saturated), and SMSP 3 carries the chain, the helper and only TWO MMA warps (pipe half loaded):
+//   14 "MMA" warps  hold the tile's residual R^T (traits x samples) in REGISTERS as the accumulator
 //                   fragments of the rank-8 update  R^T -= Delta^T X_b^T  (DMMA m8n8k4), and reuse the very
 //                   same registers as the A operand of  S^T = R^T X_b  -- the accumulator layout
 //                   C[m][2l+e] is an A fragment A[m][l] once the contraction index is read as 2l+e, so the
 //                   residual never moves: it is loaded once per tile and stored once per tile.
+//                   One lane of the last MMA warp also streams the pre-tiled X blocks (+ Gram band + SNP
+//                   ids) into a 3-stage shared-memory ring with 1-D bulk copies (TMA engine) on mbarriers.
 //   1 "chain" warp  one lane per trait: resolves the in-block Gauss-Seidel order exactly from the Gram
 //                   band (S[u] -= G[t][u] Delta[t]), evaluates mu / gam (annealed logistic) / beta and emits
 //                   -Delta.  It is the only serial dependency of the sweep (block b+1 needs Delta_b), so it
 //                   touches shared memory only; everything else of a block is done around it by the
 //   1 "helper" warp which sums the split-K partials of S, fetches the block's beta_old and c (D + cst) from the
 //                   p x q arrays one block ahead, writes gam / mu back and keeps the per-trait running sums.
-//   1 producer warp one elected lane streams the pre-tiled X blocks (+ Gram band + SNP ids) into a
-//                   3-stage shared-memory ring with 1-D bulk copies (TMA engine) on mbarriers.
 //
 // One-block look-ahead hides the serial chain behind the tensor pipe: S'_{b+1} = X_{b+1}' R_{b-1} is formed
 // while the chain of block b runs, and corrected by the cross Gram block, S_{b+1} = S'_{b+1} - G_{b+1,b} Delta_b;
@@ -38,6 +38,7 @@
 namespace aq {
 
 struct SweepParams {
+    const int* order;       // [nb * 8] sweep position -> SNP index (-1 for padding slots); same ids as in the tile images
     const double* xtiles;   // nb * ncta tile images, tile_stride doubles apart: image (b, r) at (b * ncta + r)
     size_t tile_stride;
     int nb;                 // number of SNP blocks = p_pad / 8
@@ -68,23 +69,22 @@ struct SweepParams {
 
 constexpr int kMaxCluster = 8;
 
-template <int WS_, int WT_, int MT_, int NT_, bool CL_ = false>
+template <int MT_, int NT_, bool CL_ = false>
 struct SweepCfg {
-    static constexpr int WS = WS_;  // MMA warps along samples (split-K of the S GEMM)
-    static constexpr int WT = WT_;  // MMA warps along traits
+    static constexpr int WS = 14;   // MMA warps, all along samples (split-K of the S GEMM)
     static constexpr int MT = MT_;  // 8-trait M tiles per MMA warp
     static constexpr int NT = NT_;  // 8-sample N tiles per MMA warp
     static constexpr bool kCl = CL_;  // sample-split thread-block cluster variant (n > 1008)
-    static constexpr int kMmaWarps = WS * WT;
-    static constexpr int kT = WT * MT * 8;           // traits per tile
-    static constexpr int kChainWarps = 1;            // one lane per trait
+    static constexpr int kMmaWarps = WS;
+    static constexpr int kT = MT * 8;                // traits per tile
     static constexpr int kNPad = WS * NT * 8;        // samples per CTA, padded
     static constexpr int kXS = kNPad + ((kNPad % 16 == 0) ? 8 : 0);  // tile row stride == 8 (mod 16) doubles
-    static constexpr int kThreads = 12 * 32;  // warps 3, 7, 11 (SMSP 3): chain warp(s) + producer
+    static constexpr int kThreads = 16 * 32;  // warps 3 (chain) and 7 (helper) + 14 MMA warps (two of them on SMSP 3)
     static constexpr int kStages = 3;
     static constexpr size_t kTileDoubles = (size_t)kBlk * kXS + kTileTail;
     static constexpr int kSps = 10;  // S-partial row stride (doubles): 8 SNP slots + 2 pad => conflict-free 16-byte accesses
-    static constexpr size_t kSpartDoubles = (size_t)2 * WS * kT * kSps;
+    static constexpr size_t kSpartDoubles = (size_t)WS * kT * kSps;      // [WS][kT][kSps], single-buffered (sfree barrier)
+    static constexpr size_t kSsumDoubles = (size_t)2 * kT * kSps;        // [2][kT][kSps] summed S tile for the chain
     static constexpr size_t kDbufDoubles = (size_t)2 * kT * kBlk;
     static constexpr size_t kRsqDoubles = (size_t)WS * kT;
     static constexpr size_t kIoDoubles = (size_t)2 * kBlk * 2 * kT;  // [2][kBlk][2][kT]: in beta_old, c (D + cst); out gam, mu
@@ -92,13 +92,13 @@ struct SweepCfg {
     // cluster variant only: followers' reduced S tiles and squared-norm partials land in the leader's shared memory
     static constexpr size_t kRedDoubles = kCl ? (size_t)2 * (kMaxCluster - 1) * kT * kSps : 0;
     static constexpr size_t kRsqAllDoubles = kCl ? (size_t)(kMaxCluster - 1) * kT : 0;
-    static constexpr int kNumBars = 2 * kStages + 2 + 2 + 2 + 2 + 1 + 2;  // full, empty, sdone, dready, dcons, sred, rsqbar, inready
-    static constexpr size_t kSmemBytes =
-        (kStages * kTileDoubles + kSpartDoubles + kDbufDoubles + kRsqDoubles + kIoDoubles + kRedDoubles + kRsqAllDoubles) *
-            sizeof(double) +
-        24 * sizeof(uint64_t);
+    // full, empty, sdone, dready, dcons, sred, rsqbar, inready, sfree
+    static constexpr int kNumBars = 2 * kStages + 2 + 2 + 2 + 2 + 1 + 2 + 1;
+    static constexpr size_t kSmemBytes = (kStages * kTileDoubles + kSpartDoubles + kSsumDoubles + kDbufDoubles + kRsqDoubles +
+                                          kIoDoubles + kRedDoubles + kRsqAllDoubles) *
+                                             sizeof(double) +
+                                         24 * sizeof(uint64_t);
     static_assert(kNumBars <= 24, "barrier block");
-    static_assert(kMmaWarps == 9, "9 MMA warps: three per SMSP on SMSPs 0-2");
     static_assert(kT <= 32, "one chain lane per trait");
     static_assert(kXS % 16 == 8, "row stride must be 8 mod 16 doubles");
     static_assert(kSmemBytes <= 232448, "shared memory budget (227 KB)");
@@ -111,8 +111,9 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
     constexpr bool kCl = Cfg::kCl;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* tiles = reinterpret_cast<double*>(smem_raw);
-    double* spart = tiles + kStages * Cfg::kTileDoubles;  // [2][WS][kT][kSps]
-    double* dbuf = spart + Cfg::kSpartDoubles;            // [2][kT][kBlk]  (holds -Delta)
+    double* spart = tiles + kStages * Cfg::kTileDoubles;  // [WS][kT][kSps]
+    double* ssum = spart + Cfg::kSpartDoubles;            // [2][kT][kSps]
+    double* dbuf = ssum + Cfg::kSsumDoubles;              // [2][kT][kBlk]  (holds -Delta)
     double* rsqs = dbuf + Cfg::kDbufDoubles;              // [WS][kT]
     double* iobuf = rsqs + Cfg::kRsqDoubles;              // [2][kBlk][2][kT]
     double* red = iobuf + Cfg::kIoDoubles;                // leader: [2][kMaxCluster-1][kT][kSps]
@@ -121,20 +122,25 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
     uint64_t* full = bars;                       // [kStages]  tile landed (tx bytes)
     uint64_t* empty = bars + kStages;            // [kStages]  MMA warps released the tile
     uint64_t* sdone = bars + 2 * kStages;        // [2]  this CTA's MMA warps wrote their S partials
-    uint64_t* dready = bars + 2 * kStages + 2;   // [2]  chain warps published -Delta (in every CTA of the cluster)
+    uint64_t* dready = bars + 2 * kStages + 2;   // [2]  chain warp published -Delta (in every CTA of the cluster)
     uint64_t* dcons = bars + 2 * kStages + 4;    // [2]  mode 1 only, leader: all MMA warps consumed -Delta buffer
     uint64_t* sred = bars + 2 * kStages + 6;     // [2]  leader: followers delivered their reduced S tiles
     uint64_t* rsqbar = bars + 2 * kStages + 8;   // [1]  leader: followers delivered their squared-norm partials
     uint64_t* inready = bars + 2 * kStages + 9;  // [2]  helper warp staged S and the block's inputs for the chain
+    uint64_t* sfree = bars + 2 * kStages + 11;   // [1]  helper / reducer warp has read the S partials of a block
 
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef AQ_TIMING
     long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #endif
-    // role map: SMSP 3 (wid % 4 == 3) hosts the special warps, SMSPs 0-2 the MMA warps
-    const bool is_special = (wid & 3) == 3;
-    const int mma_idx = wid - (wid >> 2);   // 0..8 for MMA warps
-    const int special_idx = wid >> 2;       // special warps: 0 chain (followers: S reducer), 1 producer, 2 helper
+    // role map: SMSPs 0-2 (wid % 4 != 3) host four MMA warps each; SMSP 3 hosts the chain (wid 3), the helper (wid 7)
+    // and MMA warps 12, 13 (wid 11, 15)
+    const int smsp = wid & 3, quad = wid >> 2;
+    const bool is_mma = smsp != 3 || quad >= 2;
+    const int mma_idx = smsp != 3 ? quad * 3 + smsp : 12 + (quad - 2);   // 0..13 for MMA warps
+    const bool is_chain = smsp == 3 && quad == 0;                          // followers: S reducer
+    const bool is_helper = smsp == 3 && quad == 1;
+    const bool is_producer = mma_idx == Cfg::kMmaWarps - 1 && is_mma;      // also streams the X tiles
     const int ncta = kCl ? P.ncta : 1;
     const int rank = kCl ? (int)cluster_ctarank() : 0;
     const int group = kCl ? (int)cluster_id_x() : (int)blockIdx.x;         // tile-loop index of this CTA (cluster)
@@ -143,12 +149,13 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], Cfg::kMmaWarps); }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&sdone[s], Cfg::kMmaWarps);
-            mbar_init(&dready[s], Cfg::kChainWarps);
+            mbar_init(&dready[s], 1);
             mbar_init(&dcons[s], Cfg::kMmaWarps * ncta);
             mbar_init(&sred[s], 1);
             mbar_init(&inready[s], 1);
         }
         mbar_init(&rsqbar[0], ncta > 1 ? ncta - 1 : 1);
+        mbar_init(&sfree[0], 1);
         fence_mbar_init();
     }
     __syncthreads();
@@ -156,30 +163,25 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
 
     const int nb = P.nb;
     const int my_tiles = (P.ntiles - group + ngroups - 1) / ngroups;
+    const long total = (long)my_tiles * nb;
     const uint32_t tile_bytes = (uint32_t)(Cfg::kTileDoubles * sizeof(double));
 
-    if (is_special && special_idx == 1) {
-        // ------------------------------------------------------------------ producer
-        if (lane == 0) {
-            const long total = (long)my_tiles * nb;
-            for (long it = 0; it < total; ++it) {
-                const int stage = (int)(it % kStages);
-                const long use = it / kStages;
-                if (use > 0) mbar_wait(&empty[stage], (uint32_t)((use - 1) & 1));
-                const int b = (int)(it % nb);
-                mbar_arrive_expect_tx(&full[stage], tile_bytes);
-                bulk_g2s(tiles + stage * Cfg::kTileDoubles, P.xtiles + ((size_t)b * ncta + rank) * P.tile_stride, tile_bytes,
-                         &full[stage]);
-            }
-        }
-    } else if (!is_special) {
+    if (is_mma) {
         // ------------------------------------------------------------------ MMA warps
-        const int ws = mma_idx % WS, wt = mma_idx / WS;
+        const int ws = mma_idx;
         const int mtid = mma_idx * 32 + lane;
+        auto load_tile = [&](long it) {  // producer duty (one lane): X tile `it` of this CTA's stream into its ring stage
+            const int stage = (int)(it % kStages);
+            const int b = (int)(it % nb);
+            mbar_arrive_expect_tx(&full[stage], tile_bytes);
+            bulk_g2s(tiles + stage * Cfg::kTileDoubles, P.xtiles + ((size_t)b * ncta + rank) * P.tile_stride, tile_bytes, &full[stage]);
+        };
+        if (is_producer && lane == 0)
+            for (long it = 0; it < kStages && it < total; ++it) load_tile(it);
         const int g = lane >> 2, l = lane & 3;
         const int i0 = ws * NT * 8;                       // first sample of this warp inside the CTA's slice
         const int ig = rank * Cfg::kNPad + i0;            // ... and inside the residual row
-        const int tr0 = wt * MT * 8;
+        constexpr int tr0 = 0;
         // lane-constant shared-memory offsets of the two operand patterns
         const int offS = g * XS + ((i0 + 2 * l) ^ ((g & 2) << 1));         // + nt*8   (16-byte loads)
         const int offU0 = l * XS + ((i0 + g) ^ ((l & 2) << 1));            // ks = 0, + nt*8
@@ -217,13 +219,14 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     const double2 xb = *reinterpret_cast<const double2*>(xt + offS + nt * 8);
+                    // (issue order keeps DMMAs on the same accumulator at least MT issue slots apart)
 #pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
-                        dmma(sa[mt][0][0], sa[mt][0][1], acc[mt][nt][0], xb.x);
-                        dmma(sa[mt][kSC - 1][0], sa[mt][kSC - 1][1], acc[mt][nt][1], xb.y);
-                    }
+                    for (int mt = 0; mt < MT; ++mt) dmma(sa[mt][0][0], sa[mt][0][1], acc[mt][nt][0], xb.x);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) dmma(sa[mt][kSC - 1][0], sa[mt][kSC - 1][1], acc[mt][nt][1], xb.y);
                 }
-                double* sp = spart + ((size_t)(gbi & 1) * WS + ws) * kT * Cfg::kSps;
+                if (gbi > 0) mbar_wait(&sfree[0], (uint32_t)((gbi - 1) & 1));  // the previous block's partials have been read
+                double* sp = spart + (size_t)ws * kT * Cfg::kSps;
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
                     double2 v;  // C fragment: S^T[trait g + 8 mt][snp 2l, 2l + 1]
@@ -272,17 +275,35 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     }
                 }
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    const double x0 = xt[offU0 + nt * 8];
-                    const double x1 = xt[offU1 + nt * 8];
+                for (int nt = 0; nt < NT; nt += 2) {
+                    // two sample tiles at a time: the two K-steps on one accumulator end up 2 MT issue slots apart
+                    constexpr int kLast = NT - 1;
+                    const int nt1 = nt + 1 < NT ? nt + 1 : kLast;
+                    const bool two = nt + 1 < NT;
+                    const double x0a = xt[offU0 + nt * 8], x1a = xt[offU1 + nt * 8];
+                    const double x0b = xt[offU0 + nt1 * 8], x1b = xt[offU1 + nt1 * 8];
 #pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
-                        dmma(acc[mt][nt][0], acc[mt][nt][1], nd[mt][0], x0);
-                        dmma(acc[mt][nt][0], acc[mt][nt][1], nd[mt][1], x1);
+                    for (int mt = 0; mt < MT; ++mt) dmma(acc[mt][nt][0], acc[mt][nt][1], nd[mt][0], x0a);
+                    if (two) {
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) dmma(acc[mt][nt1][0], acc[mt][nt1][1], nd[mt][0], x0b);
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) dmma(acc[mt][nt][0], acc[mt][nt][1], nd[mt][1], x1a);
+                    if (two) {
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) dmma(acc[mt][nt1][0], acc[mt][nt1][1], nd[mt][1], x1b);
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[stage]);
+                if (is_producer) {  // refill the stage once every MMA warp has released it
+                    if (lane == 0 && gb + kStages < total) {
+                        mbar_wait(&empty[stage], (uint32_t)((gb / kStages) & 1));
+                        load_tile(gb + kStages);
+                    }
+                    __syncwarp();
+                }
             }
             // ---- tile epilogue: store the residual, per-trait squared norms
 #pragma unroll
@@ -325,7 +346,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
             }
             asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kMmaWarps * 32) : "memory");
         }
-    } else if (special_idx == 0 && rank != 0) {
+    } else if (is_chain && rank != 0) {
         // ------------------------------------------------------------------ follower CTA: S-tile reducer warp
         // Arms this CTA's -Delta barrier for every block (the leader's asynchronous stores complete it) and, in sweep
         // mode, sums this CTA's WS split-K partials and ships the kT x 8 tile into the leader's shared memory with
@@ -340,13 +361,12 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
         const int tls = active ? tl : 0;
         const uint32_t red_leader = mapa_u32(red, 0);
         const uint32_t sred_leader[2] = {mapa_u32(&sred[0], 0), mapa_u32(&sred[1], 0)};
-        const long total = (long)my_tiles * nb;
         for (long gb = 0; gb < total; ++gb) {
             if (gb >= 2) mbar_wait(&dready[gb & 1], (uint32_t)(((gb >> 1) - 1) & 1));  // the phase of block gb - 2 is over
             if (lane == 0) mbar_arrive_expect_tx(&dready[gb & 1], Cfg::kDeltaBytes);
             if (P.mode != 0) continue;
             mbar_wait(&sdone[gb & 1], (uint32_t)((gb >> 1) & 1));
-            const double* sp = spart + (size_t)(gb & 1) * WS * kT * Cfg::kSps + tls * Cfg::kSps;
+            const double* sp = spart + tls * Cfg::kSps;
             double s[kBlk];
 #pragma unroll
             for (int t = 0; t < kBlk; ++t) s[t] = 0.0;
@@ -362,6 +382,8 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     }
                 }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sfree[0]);  // the MMA warps may overwrite the partials
             if (kH == 2) {
 #pragma unroll
                 for (int t = 0; t < kBlk; ++t) s[t] += __shfl_xor_sync(0xffffffffu, s[t], 16);
@@ -376,10 +398,10 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 }
             }
         }
-    } else if (special_idx == 2) {
+    } else if (is_helper) {
         // ------------------------------------------------------------------ helper warp (leader CTA, sweep mode)
         // Everything of a block that is NOT the serial recurrence: before the chain needs it, the split-K partials
-        // of S are summed (in place, into the ws = 0 rows) and the block's inputs beta_old and c (D + cst) are
+        // of S are summed and the block's inputs beta_old and c (D + cst) are
         // fetched from the p x q arrays into shared memory; after the chain, gam / mu go back to HBM and the
         // per-trait running sums are accumulated.  With <= 16 traits per tile the two half-warps split the work.
         if (P.mode == 0 && rank == 0) {
@@ -417,7 +439,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     }
                     mbar_wait(&sdone[g & 1], (uint32_t)((g >> 1) & 1));
                     AQ_T(4);
-                    double* sp0 = spart + (size_t)(g & 1) * WS * kT * Cfg::kSps + tls * Cfg::kSps;
+                    const double* sp0 = spart + tls * Cfg::kSps;
                     double s[kBlk];
 #pragma unroll
                     for (int t = 0; t < kBlk; ++t) s[t] = 0.0;
@@ -433,6 +455,8 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                             }
                         }
                     }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sfree[0]);  // the MMA warps may overwrite the partials
                     if (kCl && ncta > 1) {  // + the other sample slices, already reduced (and stored here) by their CTAs
                         if (lane == 0) mbar_arrive_expect_tx(&sred[g & 1], (uint32_t)(ncta - 1) * Cfg::kDeltaBytes);
                         AQ_T(5);
@@ -460,7 +484,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                             double2 v;
                             v.x = s[t];
                             v.y = s[t + 1];
-                            *reinterpret_cast<double2*>(sp0 + t) = v;
+                            *reinterpret_cast<double2*>(ssum + ((size_t)(g & 1) * kT + tl) * Cfg::kSps + t) = v;
                         }
                     }
                     double* io = iobuf + (size_t)(g & 1) * kBlk * 2 * kT;
@@ -476,7 +500,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     if (lane == 0) mbar_arrive(&inready[g & 1]);
                     AQ_T(7);
                 };
-                auto post = [&](long g) {
+                auto post = [&](long g, int pf_block) {
                     double ww[kTP], ii[kTP];
 #pragma unroll
                     for (int i = 0; i < kTP; ++i) {
@@ -485,6 +509,20 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                         ii[i] = P.i0tab[off];
                     }
                     AQ_T0();
+                    // while the chain runs: pull the rows of block b + 2 (all five p x q arrays) into L2, so that neither
+                    // this warp's loads one block from now nor the ones after that pay the HBM latency
+                    if (pf_block >= 0) {
+                        constexpr int kL = (kT * 8 > 128) ? 2 : 1;  // 128-byte lines per row segment
+                        const int* ord = P.order + (size_t)pf_block * kBlk;
+                        for (int it = lane; it < 5 * kBlk * kL; it += 32) {
+                            const int a = it / (kBlk * kL), t = (it % (kBlk * kL)) / kL, e = it % kL;
+                            const int id = __ldg(ord + t);
+                            if (id >= 0) {
+                                const double* base = a == 0 ? P.gam : a == 1 ? P.mu : a == 2 ? P.dtab : a == 3 ? P.wtab : P.i0tab;
+                                prefetch_l2(base + (size_t)id * P.q_pad + tile * kT + e * (kT - 1));
+                            }
+                        }
+                    }
                     mbar_wait(&dready[g & 1], (uint32_t)((g >> 1) & 1));
                     AQ_T(8);
                     const double* io = iobuf + (size_t)(g & 1) * kBlk * 2 * kT;
@@ -513,7 +551,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
 #pragma unroll
                     for (int i = 0; i < kTP; ++i) idc[i] = idn[i];
                     if (b + 1 < nb) pre(gb + 1);
-                    post(gb);
+                    post(gb, b + 2 < nb ? b + 2 : -1);
                 }
                 if (kH == 2) {
                     sg += __shfl_xor_sync(0xffffffffu, sg, 16);
@@ -529,7 +567,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 }
             }
         }
-    } else if (special_idx == 0) {
+    } else if (is_chain) {
         // ------------------------------------------------------------------ chain warp (one lane per trait; leader CTA)
         const int tl = lane;
         const bool active = tl < kT;
@@ -570,7 +608,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     const double* gband = tiles + stage * Cfg::kTileDoubles + kBlk * XS;
                     mbar_wait(&inready[gb & 1], (uint32_t)((gb >> 1) & 1));
                     AQ_T(0);
-                    const double* sp0 = spart + (size_t)(gb & 1) * WS * kT * Cfg::kSps + tls * Cfg::kSps;
+                    const double* sp0 = ssum + ((size_t)(gb & 1) * kT + tls) * Cfg::kSps;
                     double* io = iobuf + (size_t)(gb & 1) * kBlk * 2 * kT;
                     double s[kBlk], bo[kBlk], ap[kBlk], nd[kBlk];
 #pragma unroll
@@ -649,7 +687,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
         }
     }
 #ifdef AQ_TIMING
-    if (blockIdx.x == 0 && lane == 0 && P.timing && is_special)
+    if (blockIdx.x == 0 && lane == 0 && P.timing && (is_chain || is_helper))
         for (int i = 0; i < 10; ++i)
             if (tacc[i]) atomicAdd(reinterpret_cast<unsigned long long*>(P.timing) + i, (unsigned long long)tacc[i]);
 #endif
