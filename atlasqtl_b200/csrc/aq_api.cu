@@ -48,11 +48,13 @@ template <class C>
 CfgInfo info(int id, int ncta = 1) {
     return CfgInfo{id, C::kNPad, C::kXS, C::kT, C::kThreads, C::kSmemBytes, C::kTileDoubles, ncta};
 }
-constexpr int mt_of_nt(int nt) { return nt >= 8 ? 2 : (nt >= 6 ? 3 : 4); }  // traits / tile = 8 MT: 16, 24, 32
+// traits / tile = 8 MT: 16, 24 or 32.  Beyond 16 the helper warp handles one trait per lane (no half-warp split), which the
+// extra DSMEM hop of the clustered variant cannot afford at 7 sample tiles per warp.
+constexpr int mt_of_nt(int nt, bool cl) { return nt >= (cl ? 7 : 8) ? 2 : (nt >= 6 ? 3 : 4); }
 constexpr int kMaxNT = 9;    // single CTA: n <= 1008
 constexpr int kMaxNTCl = 8;  // clustered (the leader also buffers the followers' S tiles): n <= ncta * 896
 template <int NT, bool CL>
-using CfgOf = SweepCfg<mt_of_nt(NT), NT, CL>;
+using CfgOf = SweepCfg<mt_of_nt(NT, CL), NT, CL>;
 
 // id = nt (single CTA) or 100 + nt (clustered)
 template <int NT>
@@ -108,10 +110,12 @@ struct aq_ctx {
 
 namespace {
 
+// One launch of configuration C over `ntiles` trait tiles starting at trait k_base.  *groups (if not NULL) receives
+// the number of tiles one round of the persistent grid processes (SMs, or schedulable clusters).
 template <class C>
-int launch_sweep_t(aq_ctx* c, const SweepParams& P) {
+int launch_sweep_t(aq_ctx* c, SweepParams P, int ntiles, int k_base, int* groups) {
     static bool attr_done[64] = {false};
-    static int max_clusters[64] = {0};
+    static int max_groups[64] = {0};
     const int ncta = c->cfg.ncta;
     cudaLaunchConfig_t lc{};
     lc.blockDim = dim3(C::kThreads);
@@ -126,32 +130,62 @@ int launch_sweep_t(aq_ctx* c, const SweepParams& P) {
     lc.numAttrs = C::kCl ? 1 : 0;
     if (!attr_done[c->device]) {
         AQ_CUDA(cudaFuncSetAttribute(sweep_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
+        max_groups[c->device] = c->sm_count;
         if (C::kCl) {
             lc.gridDim = dim3(c->sm_count / ncta * ncta);
             int nc = 0;
             AQ_CUDA(cudaOccupancyMaxActiveClusters(&nc, sweep_kernel<C>, &lc));
             if (nc < 1) return fail(AQ_EUNSUPPORTED, "no thread-block cluster of the required size can be scheduled");
-            max_clusters[c->device] = nc;
+            max_groups[c->device] = nc;
         }
         attr_done[c->device] = true;
     }
-    int grid;
-    if (C::kCl) grid = std::min(c->ntiles, max_clusters[c->device]) * ncta;
-    else grid = std::min(c->ntiles, c->sm_count);
-    lc.gridDim = dim3(grid);
-    AQ_CUDA(cudaEventRecord(c->ev0, c->stream));
+    if (groups) *groups = max_groups[c->device];
+    if (ntiles <= 0) return AQ_OK;
+    P.ntiles = ntiles;
+    P.k_base = k_base;
+    lc.gridDim = dim3(std::min(ntiles, max_groups[c->device]) * ncta);
     AQ_CUDA(cudaLaunchKernelEx(&lc, sweep_kernel<C>, P));
     AQ_CUDA(cudaGetLastError());
-    AQ_CUDA(cudaEventRecord(c->ev1, c->stream));
     c->launches++;
+    return AQ_OK;
+}
+
+// The sweep over all trait tiles.  A persistent grid processes G tiles per round; a last, partly filled round would
+// cost as much as a full one, so when the leftover traits fit into one round of 8-trait tiles they are swept by the
+// MT = 1 variant of the same configuration instead (same X tiles and residual layout; an 8-trait tile is bound by the
+// serial chain and takes about half the time of a full tile).
+template <int NT, bool CL>
+int launch_sweep_cfg(aq_ctx* c, const SweepParams& P) {
+    using Main = CfgOf<NT, CL>;
+    using Tail = SweepCfg<1, NT, CL>;
+    int G = 0;
+    int rc = launch_sweep_t<Main>(c, P, 0, 0, &G);  // attributes + round size only
+    if (rc != AQ_OK) return rc;
+    const int ntiles = c->ntiles;
+    int n_main = ntiles, n_tail = 0, k_tail = 0;
+    const int rem = ntiles % G;
+    if (Main::MT > 1 && rem != 0 && !std::getenv("AQ_NO_TAIL")) {
+        k_tail = (ntiles - rem) * Main::kT;
+        const int tail_tiles = (c->q - k_tail + 7) / 8;
+        if (tail_tiles <= G) {
+            n_main = ntiles - rem;
+            n_tail = tail_tiles;
+        }
+    }
+    AQ_CUDA(cudaEventRecord(c->ev0, c->stream));
+    rc = launch_sweep_t<Main>(c, P, n_main, 0, nullptr);
+    if (rc == AQ_OK && n_tail > 0) rc = launch_sweep_t<Tail>(c, P, n_tail, k_tail, nullptr);
+    if (rc != AQ_OK) return rc;
+    AQ_CUDA(cudaEventRecord(c->ev1, c->stream));
     return AQ_OK;
 }
 
 template <int NT>
 int launch_sweep_id(aq_ctx* c, const SweepParams& P) {
-    if (c->cfg.id == NT) return launch_sweep_t<CfgOf<NT, false>>(c, P);
+    if (c->cfg.id == NT) return launch_sweep_cfg<NT, false>(c, P);
     if constexpr (NT <= kMaxNTCl)
-        if (c->cfg.id == 100 + NT) return launch_sweep_t<CfgOf<NT, true>>(c, P);
+        if (c->cfg.id == 100 + NT) return launch_sweep_cfg<NT, true>(c, P);
     if constexpr (NT < kMaxNT) return launch_sweep_id<NT + 1>(c, P);
     return fail(AQ_EUNSUPPORTED, "no kernel configuration");
 }
@@ -163,6 +197,7 @@ int launch_sweep(aq_ctx* c, int mode, double cc, double log_sig2_inv) {
     P.tile_stride = c->cfg.tile_doubles;
     P.nb = c->nb;
     P.ntiles = c->ntiles;
+    P.k_base = 0;
     P.q = c->q;
     P.q_pad = c->q_pad;
     P.ld_resid = c->ld_resid;
@@ -191,7 +226,7 @@ int launch_sweep(aq_ctx* c, int mode, double cc, double log_sig2_inv) {
         if (!tbuf) { cudaMalloc(&tbuf, 16 * sizeof(long long)); }
         long long h[16];
         cudaMemcpy(h, tbuf, sizeof(h), cudaMemcpyDeviceToHost);
-        if (mode == 0) { fprintf(stderr, "[timing of previous sweep, cycles/block]"); for (int i = 0; i < 10; ++i) fprintf(stderr, " t%d=%lld", i, h[i] / (c->nb > 0 ? c->nb : 1)); fprintf(stderr, "\n"); }
+        if (mode == 0) { fprintf(stderr, "[timing of previous sweep, cycles/block]"); for (int i = 0; i < 16; ++i) fprintf(stderr, " t%d=%lld", i, h[i] / (c->nb > 0 ? c->nb : 1)); fprintf(stderr, "\n"); }
         cudaMemset(tbuf, 0, 16 * sizeof(long long));
         P.timing = tbuf;
     }

@@ -72,6 +72,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  : "memory");
 }
 
+// 8-byte asynchronous copy global -> shared (SASS: LDGSTS), tracked per thread by commit / wait groups
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // ---------------------------------------------------------------- thread-block cluster / DSMEM PTX
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;

@@ -42,7 +42,8 @@ struct SweepParams {
     const double* xtiles;   // nb * ncta tile images, tile_stride doubles apart: image (b, r) at (b * ncta + r)
     size_t tile_stride;
     int nb;                 // number of SNP blocks = p_pad / 8
-    int ntiles;             // trait tiles = q_pad / kT
+    int ntiles;             // trait tiles of this launch
+    int k_base;             // first trait of this launch: tile i covers traits [k_base + i kT, k_base + (i + 1) kT)
     int q;                  // valid traits
     int q_pad;              // leading dimension of the p x q arrays (trait-contiguous)
     int ld_resid;           // leading dimension of resid (samples per trait row) = ncta * kNPad
@@ -88,6 +89,7 @@ struct SweepCfg {
     static constexpr size_t kDbufDoubles = (size_t)2 * kT * kBlk;
     static constexpr size_t kRsqDoubles = (size_t)WS * kT;
     static constexpr size_t kIoDoubles = (size_t)2 * kBlk * 2 * kT;  // [2][kBlk][2][kT]: in beta_old, c (D + cst); out gam, mu
+    static constexpr size_t kStgDoubles = (size_t)3 * kBlk * kT;     // [3][kBlk][kT]: gam, mu, D rows of the next block
     static constexpr uint32_t kDeltaBytes = (uint32_t)(kT * kBlk * sizeof(double));  // one -Delta block
     // cluster variant only: followers' reduced S tiles and squared-norm partials land in the leader's shared memory
     static constexpr size_t kRedDoubles = kCl ? (size_t)2 * (kMaxCluster - 1) * kT * kSps : 0;
@@ -95,7 +97,7 @@ struct SweepCfg {
     // full, empty, sdone, dready, dcons, sred, rsqbar, inready, sfree
     static constexpr int kNumBars = 2 * kStages + 2 + 2 + 2 + 2 + 1 + 2 + 1;
     static constexpr size_t kSmemBytes = (kStages * kTileDoubles + kSpartDoubles + kSsumDoubles + kDbufDoubles + kRsqDoubles +
-                                          kIoDoubles + kRedDoubles + kRsqAllDoubles) *
+                                          kIoDoubles + kStgDoubles + kRedDoubles + kRsqAllDoubles) *
                                              sizeof(double) +
                                          24 * sizeof(uint64_t);
     static_assert(kNumBars <= 24, "barrier block");
@@ -116,7 +118,8 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
     double* dbuf = ssum + Cfg::kSsumDoubles;              // [2][kT][kBlk]  (holds -Delta)
     double* rsqs = dbuf + Cfg::kDbufDoubles;              // [WS][kT]
     double* iobuf = rsqs + Cfg::kRsqDoubles;              // [2][kBlk][2][kT]
-    double* red = iobuf + Cfg::kIoDoubles;                // leader: [2][kMaxCluster-1][kT][kSps]
+    double* stg = iobuf + Cfg::kIoDoubles;                // [3][kBlk][kT]
+    double* red = stg + Cfg::kStgDoubles;                 // leader: [2][kMaxCluster-1][kT][kSps]
     double* rsq_all = red + Cfg::kRedDoubles;             // leader: [kMaxCluster-1][kT]
     uint64_t* bars = reinterpret_cast<uint64_t*>(rsq_all + Cfg::kRsqAllDoubles);
     uint64_t* full = bars;                       // [kStages]  tile landed (tx bytes)
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
 
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef AQ_TIMING
-    long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #endif
     // role map: SMSPs 0-2 (wid % 4 != 3) host four MMA warps each; SMSP 3 hosts the chain (wid 3), the helper (wid 7)
     // and MMA warps 12, 13 (wid 11, 15)
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
         long gb = 0;  // global block counter of this CTA (drives ring stage and barrier parity)
         for (int ti = 0; ti < my_tiles; ++ti) {
             const int tile = group + ti * ngroups;
-            const int k0 = tile * kT;
+            const int k0 = P.k_base + tile * kT;
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
@@ -209,7 +212,9 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 }
             auto s_phase = [&](long gbi) {
                 const int stage = (int)(gbi % kStages);
+                AQ_T0();
                 mbar_wait(&full[stage], (uint32_t)((gbi / kStages) & 1));
+                AQ_T(10);
                 const double* xt = tiles + stage * Cfg::kTileDoubles;
                 // kSC accumulator chains per M tile: a dependent DMMA issues every ~26 cycles, the pipe takes one per 16
                 constexpr int kSC = (MT >= 4) ? 1 : 2;
@@ -225,7 +230,9 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) dmma(sa[mt][kSC - 1][0], sa[mt][kSC - 1][1], acc[mt][nt][1], xb.y);
                 }
+                AQ_T(11);
                 if (gbi > 0) mbar_wait(&sfree[0], (uint32_t)((gbi - 1) & 1));  // the previous block's partials have been read
+                AQ_T(12);
                 double* sp = spart + (size_t)ws * kT * Cfg::kSps;
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
@@ -236,16 +243,19 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sdone[gbi & 1]);
+                AQ_T(13);
             };
             if (P.mode == 0) s_phase(gb);
             for (int b = 0; b < nb; ++b, ++gb) {
                 if (P.mode == 0 && b + 1 < nb) s_phase(gb + 1);
                 // ---- rank-8 update with -Delta_b
                 const int stage = (int)(gb % kStages);
+                AQ_T0();
                 if (P.mode != 0) mbar_wait(&full[stage], (uint32_t)((gb / kStages) & 1));  // sweep mode: S phase waited
                 // (followers: -Delta arrives by an async bulk copy accounted on this barrier, so a CTA-scope wait is enough;
                 // an acquire.cluster wait would invalidate L1 (CCTL.IVALL) on every block)
                 mbar_wait(&dready[gb & 1], (uint32_t)((gb >> 1) & 1));
+                AQ_T(14);
                 const double* xt = tiles + stage * Cfg::kTileDoubles;
                 const double* db = dbuf + (size_t)(gb & 1) * kT * kBlk;
                 if (kCl && rank == 0) {
@@ -297,6 +307,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[stage]);
+                AQ_T(15);
                 if (is_producer) {  // refill the stage once every MMA warp has released it
                     if (lane == 0 && gb + kStages < total) {
                         mbar_wait(&empty[stage], (uint32_t)((gb / kStages) & 1));
@@ -400,10 +411,11 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
         }
     } else if (is_helper) {
         // ------------------------------------------------------------------ helper warp (leader CTA, sweep mode)
-        // Everything of a block that is NOT the serial recurrence: before the chain needs it, the split-K partials
-        // of S are summed and the block's inputs beta_old and c (D + cst) are
-        // fetched from the p x q arrays into shared memory; after the chain, gam / mu go back to HBM and the
-        // per-trait running sums are accumulated.  With <= 16 traits per tile the two half-warps split the work.
+        // Everything of a block that is NOT the serial recurrence.  Before the chain needs them, the block's inputs
+        // beta_old and c (D + cst) are staged in shared memory (their p x q rows arrive by asynchronous copies issued
+        // one block earlier, so no HBM / L2 latency sits between "S is complete" and "the chain may start") and the
+        // split-K partials of S are summed; after the chain, gam / mu go back to HBM and the per-trait running sums
+        // are accumulated.  With <= 16 traits per tile the two half-warps split the work.
         if (P.mode == 0 && rank == 0) {
             constexpr int kH = (kT <= 16) ? 2 : 1;
             constexpr int kTP = kBlk / kH;           // SNP slots per lane
@@ -417,26 +429,42 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
             long gb = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int tile = group + ti * ngroups;
-                const int k = tile * kT + tls;
+                const int k = P.k_base + tile * kT + tls;
                 const bool valid = active && k < P.q;
                 const double sig2 = P.sig2_beta[k];
                 const double cst = -(P.log_tau[k] + P.log_sig2_inv + log(sig2)) / 2;  // src/coreLoop.cpp:56
                 double sg = 0.0, sgm2 = 0.0, sb2 = 0.0, sz = 0.0;
-                auto pre = [&](long g) {
+                // asynchronous copies (LDGSTS) of this lane's gam / mu / D elements of block `blk` into the staging buffer
+                auto stage_rows = [&](int blk) {
+                    if (active) {
+#pragma unroll
+                        for (int i = 0; i < kTP; ++i) {
+                            const int t = t0 + i;
+                            const int idt = __ldg(P.order + (size_t)blk * kBlk + t);
+                            const size_t off = (size_t)(idt < 0 ? 0 : idt) * P.q_pad + k;
+                            cp_async8(stg + (0 * kBlk + t) * kT + tl, P.gam + off);
+                            cp_async8(stg + (1 * kBlk + t) * kT + tl, P.mu + off);
+                            cp_async8(stg + (2 * kBlk + t) * kT + tl, P.dtab + off);
+                        }
+                    }
+                    cp_async_commit();
+                };
+                auto pre = [&](long g, int blk) {
                     AQ_T0();
-                    const int stage = (int)(g % kStages);
-                    mbar_wait(&full[stage], (uint32_t)((g / kStages) & 1));
-                    const int* ids = reinterpret_cast<const int*>(tiles + stage * Cfg::kTileDoubles + kBlk * XS + 128);
-                    double go[kTP], mo[kTP], dd[kTP];
+                    double* io = iobuf + (size_t)(g & 1) * kBlk * 2 * kT;
+                    cp_async_wait_all();  // issued a whole block earlier
 #pragma unroll
                     for (int i = 0; i < kTP; ++i) {
-                        const int idt = ids[t0 + i];
-                        idn[i] = idt;
-                        const size_t off = (size_t)(idt < 0 ? 0 : idt) * P.q_pad + k;
-                        go[i] = P.gam[off];
-                        mo[i] = P.mu[off];
-                        dd[i] = P.dtab[off];
+                        const int t = t0 + i;
+                        idn[i] = __ldg(P.order + (size_t)blk * kBlk + t);
+                        const double go = stg[(0 * kBlk + t) * kT + tls], mo = stg[(1 * kBlk + t) * kT + tls];
+                        const double dd = stg[(2 * kBlk + t) * kT + tls];
+                        if (active) {
+                            io[(t * 2 + 0) * kT + tl] = idn[i] >= 0 ? go * mo : 0.0;  // beta_old (0 for padding slots)
+                            io[(t * 2 + 1) * kT + tl] = P.c * (dd + cst);              // :75-77 without the mu^2 term
+                        }
                     }
+                    if (blk + 1 < nb) stage_rows(blk + 1);
                     mbar_wait(&sdone[g & 1], (uint32_t)((g >> 1) & 1));
                     AQ_T(4);
                     const double* sp0 = spart + tls * Cfg::kSps;
@@ -487,30 +515,14 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                             *reinterpret_cast<double2*>(ssum + ((size_t)(g & 1) * kT + tl) * Cfg::kSps + t) = v;
                         }
                     }
-                    double* io = iobuf + (size_t)(g & 1) * kBlk * 2 * kT;
-                    if (active) {
-#pragma unroll
-                        for (int i = 0; i < kTP; ++i) {
-                            const int t = t0 + i;
-                            io[(t * 2 + 0) * kT + tl] = idn[i] >= 0 ? go[i] * mo[i] : 0.0;  // beta_old (0 for padding slots)
-                            io[(t * 2 + 1) * kT + tl] = P.c * (dd[i] + cst);                // :75-77 without the mu^2 term
-                        }
-                    }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&inready[g & 1]);
                     AQ_T(7);
                 };
-                auto post = [&](long g, int pf_block) {
-                    double ww[kTP], ii[kTP];
-#pragma unroll
-                    for (int i = 0; i < kTP; ++i) {
-                        const size_t off = (size_t)(idc[i] < 0 ? 0 : idc[i]) * P.q_pad + k;
-                        ww[i] = P.wtab[off];
-                        ii[i] = P.i0tab[off];
-                    }
+                auto post = [&](long g, int pf_block, const double (&ww)[kTP], const double (&ii)[kTP]) {
                     AQ_T0();
-                    // while the chain runs: pull the rows of block b + 2 (all five p x q arrays) into L2, so that neither
-                    // this warp's loads one block from now nor the ones after that pay the HBM latency
+                    // while the chain runs: pull the rows of block b + 2 (all five p x q arrays) into L2, so that the copies
+                    // and loads issued for it one block from now are L2 hits
                     if (pf_block >= 0) {
                         constexpr int kL = (kT * 8 > 128) ? 2 : 1;  // 128-byte lines per row segment
                         const int* ord = P.order + (size_t)pf_block * kBlk;
@@ -519,7 +531,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                             const int id = __ldg(ord + t);
                             if (id >= 0) {
                                 const double* base = a == 0 ? P.gam : a == 1 ? P.mu : a == 2 ? P.dtab : a == 3 ? P.wtab : P.i0tab;
-                                prefetch_l2(base + (size_t)id * P.q_pad + tile * kT + e * (kT - 1));
+                                prefetch_l2(base + (size_t)id * P.q_pad + P.k_base + tile * kT + e * (kT - 1));
                             }
                         }
                     }
@@ -546,12 +558,19 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     }
                     AQ_T(9);
                 };
-                pre(gb);
+                stage_rows(0);
+                pre(gb, 0);
                 for (int b = 0; b < nb; ++b, ++gb) {
+                    double ww[kTP], ii[kTP];  // requested before the next block is prepared, consumed after the chain
 #pragma unroll
-                    for (int i = 0; i < kTP; ++i) idc[i] = idn[i];
-                    if (b + 1 < nb) pre(gb + 1);
-                    post(gb, b + 2 < nb ? b + 2 : -1);
+                    for (int i = 0; i < kTP; ++i) {
+                        idc[i] = idn[i];
+                        const size_t off = (size_t)(idc[i] < 0 ? 0 : idc[i]) * P.q_pad + k;
+                        ww[i] = P.wtab[off];
+                        ii[i] = P.i0tab[off];
+                    }
+                    if (b + 1 < nb) pre(gb + 1, b + 1);
+                    post(gb, b + 2 < nb ? b + 2 : -1, ww, ii);
                 }
                 if (kH == 2) {
                     sg += __shfl_xor_sync(0xffffffffu, sg, 16);
@@ -591,7 +610,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
         long gb = 0;
         for (int ti = 0; ti < my_tiles; ++ti) {
             const int tile = group + ti * ngroups;
-            const int k = tile * kT + tls;
+            const int k = P.k_base + tile * kT + tls;
             const bool valid = active && k < P.q;
             if (P.mode == 0) {
                 // ---- sweep: only the serial recurrence lives here; inputs arrive through shared memory (helper warp)
@@ -687,8 +706,8 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
         }
     }
 #ifdef AQ_TIMING
-    if (blockIdx.x == 0 && lane == 0 && P.timing && (is_chain || is_helper))
-        for (int i = 0; i < 10; ++i)
+    if (blockIdx.x == 0 && lane == 0 && P.timing && (is_chain || is_helper || wid == 0))
+        for (int i = 0; i < 16; ++i)
             if (tacc[i]) atomicAdd(reinterpret_cast<unsigned long long*>(P.timing) + i, (unsigned long long)tacc[i]);
 #endif
     if (kCl) {

@@ -50,10 +50,19 @@ def _cpu_sweep(native, X, Y, si, order):
     # sample-split thread-block clusters (2 / 4 / 8 CTAs), every clustered configuration, several tiles per cluster
     (1009, 17, 40), (1100, 20, 70), (1250, 12, 30), (1400, 16, 20), (1500, 25, 50), (1728, 9, 17),
     (1800, 12, 40), (2500, 20, 33), (3000, 24, 50), (3456, 8, 16), (3600, 10, 30), (5000, 16, 60), (6912, 8, 24),
+    # more tiles than one round of the persistent grid: full rounds by the main kernel + leftover traits by the 8-trait one
+    (100, 16, 4776), (1000, 9, 2400), (1200, 12, 1806),
 ])
-def test_ragged_shapes_and_all_configs(oracle_built, n, p, q):
+@pytest.mark.parametrize("tail", [True, False], ids=["tail8", "notail"])
+def test_ragged_shapes_and_all_configs(oracle_built, monkeypatch, n, p, q, tail):
+    """tail8: leftover traits (here usually ALL traits: fewer tiles than SMs) go through the 8-trait tile kernel;
+    notail (AQ_NO_TAIL): every tile through the configuration's full-size kernel."""
     from atlasqtl_b200.device import SweepContext
     native = oracle_built
+    if tail:
+        monkeypatch.delenv("AQ_NO_TAIL", raising=False)
+    else:
+        monkeypatch.setenv("AQ_NO_TAIL", "1")
     rng = np.random.default_rng(n + p + q)
     X = rng.normal(size=(n, p))
     X = np.asfortranarray((X - X.mean(0)) / X.std(0, ddof=1))
