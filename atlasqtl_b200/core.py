@@ -146,12 +146,14 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
     gives its position among the q_total = shr_fac_inv traits so that per-trait hyper / init vectors
     (length q_total) can be sliced.  `order_fn(it, p)` supplies shuffled_ind per iteration (identity
     by default, like the reference, :162).  Keyword-only arguments are extensions; the R-facing ones
-    keep their meaning.  Missing values in Y (coreDualMisLoop) are not supported by this build.
+    keep their meaning.  Missing values in Y (NaN) select the coreDualMisLoop path (:19-38, :172-175), n <= 2048.
     """
     if batch != "y":
         raise ValueError("Batch scheme not defined. Exit.")  # only the C++ path is replaced (:179-232)
-    if np.isnan(Y).any():
-        raise NotImplementedError("missing responses (coreDualMisLoop) are not covered by this build")
+    mis_pat = None
+    if np.isnan(Y).any():  # :19-33 (X_norm_sq and the per-trait Gram corrections live on the device)
+        mis_pat = np.where(np.isnan(Y), 0.0, 1.0)
+        Y = np.where(np.isnan(Y), 0.0, Y)
     if checkpoint_path is not None or trace_path is not None:
         raise NotImplementedError("checkpoint_path / trace_path are host-side I/O outside this path")
     comm = comm or SerialComm()
@@ -214,13 +216,28 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
         if order_fn is not None:
             order = np.ascontiguousarray(order_fn(1, p), dtype=np.int32)
         ctx.set_order(order)
-        sums = ctx.set_state(gam0, mu0)  # beta_vb, residual, and the sums m2_beta / kappa_vb need (:112-115)
+        if mis_pat is None:
+            n_eff = n
+            sums = ctx.set_state(gam0, mu0)  # beta_vb, residual, and the sums m2_beta / kappa_vb need (:112-115)
+        else:
+            n_eff = ctx.set_missing(mis_pat)  # colSums(mis_pat): update_eta_vb_ R/update_vb.R:131, e_y_ R/elbo.R:141
+            sums = ctx.set_state_mis(gam0, mu0)
+            # m2_beta <- update_m2_beta_(..., sweep = TRUE) with the q-vector sig2_beta_vb of the init (:113)
+            sums["colsum_m2"] = sums["colsum_gam_mu2"] + sig2_beta_vb * sums["colsum_gam"]
+            sums["colsum_xn_m2"] = sums["colsum_xn_gam_mu2"] + sig2_beta_vb * sums["colsum_xn_gam"]
         del gam0, mu0
         ctx.refresh_tables(theta_vb, zeta_vb, c_next=c)  # :61-63
         sig2_beta_for_m2 = sig2_beta_vb  # m2_beta always pairs gam/mu with the sig2_beta_vb of their sweep (:113,:235)
-        glob = comm.allreduce_sum(np.array([sums["colsum_gam"].sum(),
-                                            np.dot(tau_vb, sums["colsum_gam_mu2"] + sig2_beta_for_m2 * sums["colsum_gam"]),
-                                            zeta_vb.sum()]))
+
+        def m2_of(sm):  # colSums(m2_beta)
+            return sm["colsum_m2"] if "colsum_m2" in sm else sm["colsum_gam_mu2"] + sig2_beta_for_m2 * sm["colsum_gam"]
+
+        def kappa_rate(sm, s_inv):  # the bracket of update_kappa_vb_ (R/update_vb.R:144-146 / :149-154)
+            if mis_pat is None:
+                return sm["resid_sq"] + (n - 1 + s_inv) * m2_of(sm) - (n - 1) * sm["colsum_beta2"]
+            return sm["resid_sq"] + s_inv * m2_of(sm) + sm["colsum_xn_m2"] - sm["colsum_xn_beta2"]
+
+        glob = comm.allreduce_sum(np.array([sums["colsum_gam"].sum(), np.dot(tau_vb, m2_of(sums)), zeta_vb.sum()]))
         sum_gam, tau_dot_m2, sum_zeta = (float(v) for v in glob)
 
         converged = False
@@ -237,15 +254,13 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
             if verbose != 0 and comm.rank == 0 and (it == 1 or it % max(5, batch_conv) == 0):
                 print(f"Iteration {it}... ")
 
-            colsum_m2 = sums["colsum_gam_mu2"] + sig2_beta_for_m2 * sums["colsum_gam"]
             nu_vb = c * (nu + sum_gam / 2) - c + 1  # :134
             rho_vb = c * (rho + tau_dot_m2 / 2)  # :135 (uses the tau_vb of the previous iteration)
             sig2_inv_vb = nu_vb / rho_vb  # :137
-            eta_vb = c * (eta + n / 2 + sums["colsum_gam"] / 2) - c + 1  # :141
-            kappa_vb = c * (kappa + (sums["resid_sq"] + (n - 1 + sig2_inv_vb) * colsum_m2
-                                     - (n - 1) * sums["colsum_beta2"]) / 2)  # :142, R/update_vb.R:144-146
+            eta_vb = c * (eta + n_eff / 2 + sums["colsum_gam"] / 2) - c + 1  # :141
+            kappa_vb = c * (kappa + kappa_rate(sums, sig2_inv_vb) / 2)  # :142
             tau_vb = eta_vb / kappa_vb  # :145
-            sig2_beta_vb = 1 / (c * (n - 1 + sig2_inv_vb) * tau_vb)  # :147
+            sig2_beta_vb = 1 / (c * (n - 1 + sig2_inv_vb) * tau_vb)  # :147 (p x q, formed on the device, if Y has NAs)
             log_tau_vb = sp.digamma(eta_vb) - np.log(kappa_vb)  # :149
             log_sig2_inv_vb = float(sp.digamma(nu_vb) - math.log(rho_vb))  # :150
 
@@ -253,9 +268,14 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
                 ctx.set_order(np.ascontiguousarray(order_fn(it, p), dtype=np.int32))  # :160-163
 
             # ---- the sweep (:167-170) with the fused reductions
-            sums = ctx.sweep(c, log_sig2_inv_vb, tau_vb, log_tau_vb, sig2_beta_vb)
+            if mis_pat is None:
+                sums = ctx.sweep(c, log_sig2_inv_vb, tau_vb, log_tau_vb, sig2_beta_vb)
+            else:  # coreDualMisLoop (:172-175)
+                sums = ctx.sweep_mis(c, log_sig2_inv_vb, sig2_inv_vb, tau_vb, log_tau_vb)
+                sums["colsum_m2"] = sums["colsum_gam_mu2"] + sums["colsum_sig2b_gam"]  # update_m2_beta_ with p x q sig2_beta_vb
+                sums["colsum_xn_m2"] = sums["colsum_xn_gam_mu2"] + sums["colsum_xn_sig2b_gam"]
             sig2_beta_for_m2 = sig2_beta_vb
-            colsum_m2 = sums["colsum_gam_mu2"] + sig2_beta_vb * sums["colsum_gam"]  # :235
+            colsum_m2 = m2_of(sums)  # :235
             rows = ctx.rowsums_zpart()
             glob = comm.allreduce_sum(np.concatenate([rows, [sums["colsum_gam"].sum(), np.dot(tau_vb, colsum_m2)]]))
             rowsum_zpart, sum_gam, tau_dot_m2 = glob[:p], float(glob[p]), float(glob[p + 1])
@@ -308,9 +328,8 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
 
             if want_elbo:
                 # ---- elbo_global_local_ (:440-495): c = 1 re-derivations from the post-sweep sums (:456-467)
-                eta_e = eta + n / 2 + sums["colsum_gam"] / 2
-                kappa_e = kappa + (sums["resid_sq"] + (n - 1 + sig2_inv_vb) * colsum_m2
-                                   - (n - 1) * sums["colsum_beta2"]) / 2
+                eta_e = eta + n_eff / 2 + sums["colsum_gam"] / 2
+                kappa_e = kappa + kappa_rate(sums, sig2_inv_vb) / 2
                 nu_e = nu + sum_gam / 2
                 rho_e = rho + tau_dot_m2 / 2
                 log_tau_e = sp.digamma(eta_e) - np.log(kappa_e)
@@ -318,10 +337,14 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
                 log_sig02_inv_vb = float(sp.digamma(nu_s0_vb) - math.log(rho_s0_vb))
                 log_xi_inv_vb = float(sp.digamma(nu_xi_inv_vb) - math.log(rho_xi_inv_vb))
                 # A: e_y_ (R/elbo.R:135-146)
-                A = np.sum(-n / 2 * math.log(2 * math.pi) + n / 2 * log_tau_e
+                A = np.sum(-n_eff / 2 * math.log(2 * math.pi) + n_eff / 2 * log_tau_e
                            - tau_vb * (kappa_e - colsum_m2 * sig2_inv_vb / 2 - kappa))
                 # B: e_beta_gamma_ (R/elbo.R:10-34): per-trait terms from the column sums + the device part
-                B_loc = (np.sum(sums["colsum_gam"] * (log_sig2_inv_e / 2 + log_tau_e / 2 + (np.log(sig2_beta_vb) + 1) / 2))
+                if mis_pat is None:
+                    gam_log_s2b = sums["colsum_gam"] * np.log(sig2_beta_vb)
+                else:
+                    gam_log_s2b = sums["colsum_gam_logsig2b"]  # sum_j gam log sig2_beta_vb(j,k) (R/elbo.R:28-30)
+                B_loc = (np.sum(sums["colsum_gam"] * (log_sig2_inv_e / 2 + log_tau_e / 2 + 0.5) + gam_log_s2b / 2)
                          - np.sum(colsum_m2 * tau_vb) * sig2_inv_vb / 2 + elbo_b_dev - p * q * sig2_zeta_vb / 2
                          - q * np.sum(sig2_theta_vb) / 2)
                 # D: e_zeta_ without its constants (R/elbo.R:153-161);  E: e_tau_ (:63-68)

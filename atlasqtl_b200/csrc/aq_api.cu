@@ -11,6 +11,7 @@
 
 #include "../../include/atlasqtl_b200.h"
 #include "aq_internal.h"
+#include "aq_mis.cuh"
 #include "aq_stream.cuh"
 #include "aq_sweep.cuh"
 
@@ -101,6 +102,10 @@ struct aq_ctx {
     int stage_cols = 0;
     size_t n_partials = 0;
     int* order_dev = nullptr;
+    // missing responses (aq_set_missing): bit masks, X_norm_sq, per-trait observation counts and the sums of the NA kernels
+    unsigned long long* mask = nullptr;
+    double *xnsq = nullptr, *n_obs = nullptr, *mis_out = nullptr;
+    bool has_mis = false;
     std::vector<int32_t> order, order_pad;
     std::vector<double> hbuf;   // pinned-size-agnostic host scratch
     bool have_state = false, have_tables = false;
@@ -354,6 +359,9 @@ int aq_destroy(aq_ctx* c) {
     for (double* b : bufs)
         if (b) cudaFree(b);
     if (c->order_dev) cudaFree(c->order_dev);
+    if (c->mask) cudaFree(c->mask);
+    for (double* b : {c->xnsq, c->n_obs, c->mis_out})
+        if (b) cudaFree(b);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : {c->evr0, c->evr1, c->evt0, c->evt1})
@@ -491,6 +499,7 @@ int aq_set_order(aq_ctx* c, const int32_t* shuffled_ind) {
 int aq_set_state(aq_ctx* c, const double* gam_vb, const double* mu_beta_vb, double* colsum_gam, double* colsum_gam_mu2,
                  double* colsum_beta2, double* resid_sq) {
     if (!c || !gam_vb || !mu_beta_vb) return fail(AQ_EINVAL, "aq_set_state: NULL argument");
+    if (c->has_mis) return fail(AQ_ESTATE, "aq_set_state: this context has missing responses, use aq_set_state_mis");
     AQ_CUDA(cudaSetDevice(c->device));
     int rc = upload_pxq(c, gam_vb, c->gam);
     if (rc != AQ_OK) return rc;
@@ -560,6 +569,7 @@ int aq_sweep(aq_ctx* c, double cc, double log_sig2_inv_vb, const double* tau_vb,
              const double* sig2_beta_vb, double* colsum_gam, double* colsum_gam_mu2, double* colsum_beta2,
              double* resid_sq, double* colsum_zpart) {
     if (!c || !tau_vb || !log_tau_vb || !sig2_beta_vb) return fail(AQ_EINVAL, "aq_sweep: NULL argument");
+    if (c->has_mis) return fail(AQ_ESTATE, "aq_sweep: this context has missing responses, use aq_sweep_mis");
     if (!c->have_state) return fail(AQ_ESTATE, "aq_sweep before aq_set_state");
     if (!c->have_tables) return fail(AQ_ESTATE, "aq_sweep before aq_refresh_tables");
     if (!(cc > 0.0)) return fail(AQ_EINVAL, "aq_sweep: c must be positive");
@@ -598,6 +608,128 @@ int aq_rowsums_zpart(aq_ctx* c, double* rowsum_zpart) {
     int rc = aq_rowsums_zpart_dev(c, &dev);
     if (rc != AQ_OK) return rc;
     AQ_CUDA(cudaMemcpy(rowsum_zpart, dev, sizeof(double) * c->p, cudaMemcpyDeviceToHost));
+    return AQ_OK;
+}
+
+// ---------------------------------------------------------------- missing responses (coreDualMisLoop)
+namespace {
+int launch_mis(aq_ctx* c, int mode, double cc, double log_sig2_inv, double sig2_inv) {
+    MisParams P;
+    P.xraw = c->xraw;
+    P.order = c->order_dev;
+    P.mask = c->mask;
+    P.n = c->n;
+    P.p_pad = c->p_pad;
+    P.q = c->q;
+    P.q_pad = c->q_pad;
+    P.ld_resid = c->ld_resid;
+    P.resid = c->resid;
+    P.gam = c->gam;
+    P.mu = c->mu;
+    P.dtab = c->dtab;
+    P.wtab = c->wtab;
+    P.i0tab = c->i0tab;
+    P.xnsq = c->xnsq;
+    P.tau = c->tvec;
+    P.log_tau = c->tvec + c->q_pad;
+    P.c = cc;
+    P.log_sig2_inv = log_sig2_inv;
+    P.sig2_inv = sig2_inv;
+    P.out = c->mis_out;
+    P.mode = mode;
+    const int warps = 8, grid = (c->q + warps - 1) / warps;
+    const int M = (c->n + 31) / 32;
+    AQ_CUDA(cudaEventRecord(c->ev0, c->stream));
+    if (M <= 4) mis_sweep_kernel<4><<<grid, warps * 32, 0, c->stream>>>(P);
+    else if (M <= 8) mis_sweep_kernel<8><<<grid, warps * 32, 0, c->stream>>>(P);
+    else if (M <= 16) mis_sweep_kernel<16><<<grid, warps * 32, 0, c->stream>>>(P);
+    else if (M <= 32) mis_sweep_kernel<32><<<grid, warps * 32, 0, c->stream>>>(P);
+    else mis_sweep_kernel<64><<<grid, warps * 32, 0, c->stream>>>(P);
+    AQ_CUDA(cudaGetLastError());
+    AQ_CUDA(cudaEventRecord(c->ev1, c->stream));
+    c->launches++;
+    return AQ_OK;
+}
+
+int fetch_mis(aq_ctx* c, const int* rows, double* const* outs, int nout) {
+    c->hbuf.resize((size_t)kMisOutputs * c->q_pad);
+    AQ_CUDA(cudaMemcpyAsync(c->hbuf.data(), c->mis_out, sizeof(double) * kMisOutputs * (size_t)c->q_pad,
+                            cudaMemcpyDeviceToHost, c->stream));
+    AQ_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < nout; ++i)
+        if (outs[i]) std::memcpy(outs[i], c->hbuf.data() + (size_t)rows[i] * c->q_pad, sizeof(double) * c->q);
+    return AQ_OK;
+}
+}  // namespace
+
+int aq_set_missing(aq_ctx* c, const double* mis_pat, double* n_obs) {
+    if (!c || !mis_pat) return fail(AQ_EINVAL, "aq_set_missing: NULL argument");
+    if (c->n > 2048) return fail(AQ_EUNSUPPORTED, "aq_set_missing: the missing-response kernel covers n <= 2048");
+    AQ_CUDA(cudaSetDevice(c->device));
+    const size_t pq = (size_t)c->p_pad * c->q_pad;
+    if (!c->mask) {
+        AQ_CUDA(cudaMalloc((void**)&c->mask, sizeof(unsigned long long) * 32 * (size_t)c->q_pad));
+        AQ_CUDA(cudaMalloc((void**)&c->xnsq, sizeof(double) * pq));
+        AQ_CUDA(cudaMalloc((void**)&c->n_obs, sizeof(double) * c->q_pad));
+        AQ_CUDA(cudaMalloc((void**)&c->mis_out, sizeof(double) * kMisOutputs * (size_t)c->q_pad));
+    }
+    AQ_CUDA(cudaMemsetAsync(c->xnsq, 0, sizeof(double) * pq, c->stream));
+    AQ_CUDA(cudaMemsetAsync(c->mask, 0, sizeof(unsigned long long) * 32 * (size_t)c->q_pad, c->stream));
+    // the n x q pattern goes through the residual buffer (same [q][ld] orientation, ld >= n), which is rebuilt by set_state
+    double* tmp = c->resid;
+    AQ_CUDA(cudaMemcpyAsync(tmp, mis_pat, sizeof(double) * (size_t)c->n * c->q, cudaMemcpyHostToDevice, c->stream));
+    pack_mask_kernel<<<(c->q + 7) / 8, 256, 0, c->stream>>>(tmp, c->n, c->q, c->ld_resid, c->mask, c->ymat, c->n_obs);
+    AQ_CUDA(cudaGetLastError());
+    c->launches++;
+    c->has_mis = true;
+    c->have_state = false;
+    int rc = launch_mis(c, /*mode=*/2, 1.0, 0.0, 0.0);   // X_norm_sq = crossprod(X^2, mis_pat)
+    if (rc != AQ_OK) return rc;
+    if (n_obs) AQ_CUDA(cudaMemcpyAsync(n_obs, c->n_obs, sizeof(double) * c->q, cudaMemcpyDeviceToHost, c->stream));
+    AQ_CUDA(cudaStreamSynchronize(c->stream));
+    return AQ_OK;
+}
+
+int aq_set_state_mis(aq_ctx* c, const double* gam_vb, const double* mu_beta_vb, double* colsum_gam,
+                     double* colsum_gam_mu2, double* colsum_beta2, double* resid_sq, double* colsum_xn_gam,
+                     double* colsum_xn_gam_mu2, double* colsum_xn_beta2) {
+    if (!c || !gam_vb || !mu_beta_vb) return fail(AQ_EINVAL, "aq_set_state_mis: NULL argument");
+    if (!c->has_mis) return fail(AQ_ESTATE, "aq_set_state_mis before aq_set_missing");
+    AQ_CUDA(cudaSetDevice(c->device));
+    int rc = upload_pxq(c, gam_vb, c->gam);
+    if (rc != AQ_OK) return rc;
+    rc = upload_pxq(c, mu_beta_vb, c->mu);
+    if (rc != AQ_OK) return rc;
+    AQ_CUDA(cudaMemcpyAsync(c->resid, c->ymat, sizeof(double) * (size_t)c->q_pad * c->ld_resid, cudaMemcpyDeviceToDevice,
+                            c->stream));
+    rc = launch_mis(c, /*mode=*/1, 1.0, 0.0, 0.0);
+    if (rc != AQ_OK) return rc;
+    c->have_state = true;
+    const int rows[7] = {kMisGam, kMisGamMu2, kMisS2Gam, kMisRsq, kMisXnS2Gam, kMisXnGamMu2, kMisXnBeta2};
+    double* outs[7] = {colsum_gam, colsum_gam_mu2, colsum_beta2, resid_sq, colsum_xn_gam, colsum_xn_gam_mu2, colsum_xn_beta2};
+    return fetch_mis(c, rows, outs, 7);
+}
+
+int aq_sweep_mis(aq_ctx* c, double cc, double log_sig2_inv_vb, double sig2_inv_vb, const double* tau_vb,
+                 const double* log_tau_vb, double* colsum_gam, double* colsum_gam_mu2, double* colsum_sig2b_gam,
+                 double* colsum_xn_gam_mu2, double* colsum_xn_sig2b_gam, double* colsum_xn_beta2, double* resid_sq,
+                 double* colsum_zpart, double* colsum_gam_logsig2b) {
+    if (!c || !tau_vb || !log_tau_vb) return fail(AQ_EINVAL, "aq_sweep_mis: NULL argument");
+    if (!c->has_mis) return fail(AQ_ESTATE, "aq_sweep_mis before aq_set_missing");
+    if (!c->have_state) return fail(AQ_ESTATE, "aq_sweep_mis before aq_set_state_mis");
+    if (!c->have_tables) return fail(AQ_ESTATE, "aq_sweep_mis before aq_refresh_tables");
+    if (!(cc > 0.0) || !(sig2_inv_vb > 0.0)) return fail(AQ_EINVAL, "aq_sweep_mis: c and sig2_inv_vb must be positive");
+    AQ_CUDA(cudaSetDevice(c->device));
+    AQ_CUDA(cudaMemcpyAsync(c->tvec, tau_vb, sizeof(double) * c->q, cudaMemcpyHostToDevice, c->stream));
+    AQ_CUDA(cudaMemcpyAsync(c->tvec + c->q_pad, log_tau_vb, sizeof(double) * c->q, cudaMemcpyHostToDevice, c->stream));
+    int rc = launch_mis(c, /*mode=*/0, cc, log_sig2_inv_vb, sig2_inv_vb);
+    if (rc != AQ_OK) return rc;
+    const int rows[9] = {kMisGam, kMisGamMu2, kMisS2Gam, kMisXnGamMu2, kMisXnS2Gam, kMisXnBeta2, kMisRsq, kMisZ, kMisGamLogS2};
+    double* outs[9] = {colsum_gam, colsum_gam_mu2, colsum_sig2b_gam, colsum_xn_gam_mu2, colsum_xn_sig2b_gam,
+                       colsum_xn_beta2, resid_sq, colsum_zpart, colsum_gam_logsig2b};
+    rc = fetch_mis(c, rows, outs, 9);
+    if (rc != AQ_OK) return rc;
+    AQ_CUDA(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
     return AQ_OK;
 }
 

@@ -91,6 +91,37 @@ class SweepContext:
                                       *[_lib.dptr(v) for v in vecs], *[_lib.dptr(x) for x in o]))
         return dict(colsum_gam=o[0], colsum_gam_mu2=o[1], colsum_beta2=o[2], resid_sq=o[3], colsum_zpart=o[4])
 
+    # ---- missing responses (coreDualMisLoop; include/atlasqtl_b200.h)
+    def set_missing(self, mis_pat):
+        """mis_pat: n x q_local, 1 where y is observed, 0 where missing.  Returns colSums(mis_pat)."""
+        m = _lib.fmat(mis_pat)
+        if m.shape != (self.n, self.q):
+            raise ValueError("mis_pat must be n x q_local")
+        n_obs = np.empty(self.q)
+        _lib.check(self._lib.aq_set_missing(self._ctx, _lib.dptr(m), _lib.dptr(n_obs)))
+        return n_obs
+
+    def set_state_mis(self, gam_vb, mu_beta_vb):
+        g, m = _lib.fmat(gam_vb), _lib.fmat(mu_beta_vb)
+        if g.shape != (self.p, self.q) or m.shape != (self.p, self.q):
+            raise ValueError("gam_vb / mu_beta_vb must be p x q")
+        o = self._qvecs(7)
+        _lib.check(self._lib.aq_set_state_mis(self._ctx, _lib.dptr(g), _lib.dptr(m), *[_lib.dptr(x) for x in o]))
+        return dict(zip(("colsum_gam", "colsum_gam_mu2", "colsum_beta2", "resid_sq", "colsum_xn_gam",
+                         "colsum_xn_gam_mu2", "colsum_xn_beta2"), o))
+
+    def sweep_mis(self, c, log_sig2_inv_vb, sig2_inv_vb, tau_vb, log_tau_vb):
+        vecs = [np.ascontiguousarray(v, dtype=np.float64) for v in (tau_vb, log_tau_vb)]
+        for v in vecs:
+            if v.shape != (self.q,):
+                raise ValueError("per-trait vectors must have length q_local")
+        o = self._qvecs(9)
+        _lib.check(self._lib.aq_sweep_mis(self._ctx, ctypes.c_double(c), ctypes.c_double(log_sig2_inv_vb),
+                                          ctypes.c_double(sig2_inv_vb), *[_lib.dptr(v) for v in vecs],
+                                          *[_lib.dptr(x) for x in o]))
+        return dict(zip(("colsum_gam", "colsum_gam_mu2", "colsum_sig2b_gam", "colsum_xn_gam_mu2", "colsum_xn_sig2b_gam",
+                         "colsum_xn_beta2", "resid_sq", "colsum_zpart", "colsum_gam_logsig2b"), o))
+
     def rowsums_zpart(self):
         r = np.empty(self.p)
         _lib.check(self._lib.aq_rowsums_zpart(self._ctx, _lib.dptr(r)))

@@ -126,6 +126,41 @@ int aq_sweep(aq_ctx* ctx, double c, double log_sig2_inv_vb, const double* tau_vb
 int aq_rowsums_zpart(aq_ctx* ctx, double* rowsum_zpart);
 int aq_rowsums_zpart_dev(aq_ctx* ctx, double** rowsum_zpart_dev);
 
+/*
+ * Missing responses: the reference's second native entry, `.Call _atlasqtl_coreDualMisLoop` (16 SEXP args,
+ * src/RcppExports.cpp:41-63; src/coreLoop.cpp:91-138) and its set-up (R/atlasqtl_global_local_core.R:19-33).
+ *
+ * aq_set_missing: mis_pat is the reference's n x q_local matrix ifelse(is.na(Y), 0, 1).  The Y handed to aq_create
+ * may hold anything in the missing positions; they are zeroed here (:22).  Replaces X_norm_sq <- crossprod(X^2,
+ * mis_pat) and the list cp_X_rm of q p x p matrices (:23-32): in sample space the per-trait Gram cp_X - cp_X_rm[[k]]
+ * is X' diag(mis_k) X, i.e. a residual kept at zero in the missing rows.  n_obs (may be NULL) returns colSums(mis_pat)
+ * (update_eta_vb_, R/update_vb.R:131; e_y_, R/elbo.R:141).  n <= 2048 in this build.
+ * After this call the context must be driven through aq_set_state_mis / aq_sweep_mis; all other entry points
+ * (aq_set_order, aq_refresh_tables, aq_rowsums_zpart, aq_get_state, aq_get_residual) are shared.
+ *
+ * aq_set_state_mis: as aq_set_state, with r_k = mis_k o (y_k - X beta_k); xn = X_norm_sq.  Extra per-trait sums
+ * (any may be NULL): colsum_xn_gam = sum_j xn gam, colsum_xn_gam_mu2 = sum_j xn gam mu^2, colsum_xn_beta2 = sum_j xn
+ * beta^2 -- with them update_kappa_vb_'s missing-value branch (R/update_vb.R:149-154) is
+ *   kappa_vb = c (kappa + (resid_sq + sig2_inv colSums(m2) + colSums(xn m2) - colsum_xn_beta2) / 2).
+ *
+ * aq_sweep_mis: one sweep of coreDualMisLoop in the order of aq_set_order, with the p x q
+ * sig2_beta_vb(j,k) = 1 / (c (xn(j,k) + sig2_inv_vb) tau_vb[k]) of update_sig2_beta_vb_ (R/update_vb.R:47) formed on
+ * the fly.  Outputs (length q_local, any may be NULL) on the post-sweep state:
+ *   colsum_gam, colsum_gam_mu2, resid_sq, colsum_zpart       as aq_sweep
+ *   colsum_sig2b_gam      sum_j sig2_beta_jk gam;   colSums(m2_beta) = colsum_gam_mu2 + colsum_sig2b_gam
+ *   colsum_xn_gam_mu2, colsum_xn_sig2b_gam                    colSums(xn m2_beta) is their sum
+ *   colsum_xn_beta2       sum_j xn beta^2
+ *   colsum_gam_logsig2b   sum_j gam log sig2_beta_jk           (e_beta_gamma_, R/elbo.R:28-30)
+ */
+int aq_set_missing(aq_ctx* ctx, const double* mis_pat, double* n_obs);
+int aq_set_state_mis(aq_ctx* ctx, const double* gam_vb, const double* mu_beta_vb, double* colsum_gam,
+                     double* colsum_gam_mu2, double* colsum_beta2, double* resid_sq, double* colsum_xn_gam,
+                     double* colsum_xn_gam_mu2, double* colsum_xn_beta2);
+int aq_sweep_mis(aq_ctx* ctx, double c, double log_sig2_inv_vb, double sig2_inv_vb, const double* tau_vb,
+                 const double* log_tau_vb, double* colsum_gam, double* colsum_gam_mu2, double* colsum_sig2b_gam,
+                 double* colsum_xn_gam_mu2, double* colsum_xn_sig2b_gam, double* colsum_xn_beta2, double* resid_sq,
+                 double* colsum_zpart, double* colsum_gam_logsig2b);
+
 /* Count of kernel launches issued through this context so far (bench.py's gpu_launches). */
 int64_t aq_launch_count(const aq_ctx* ctx);
 

@@ -202,3 +202,42 @@ void oracle_residual(int n, int p, int q, const double* X, const double* Y, cons
     }
   }
 }
+
+/* Missing responses: coreDualMisLoop (reference src/coreLoop.cpp:91-138) in sample space.
+ * mis n x q holds 1 where y_ik is observed, 0 where it is missing (R/atlasqtl_global_local_core.R:21);
+ * the reference's per-trait Gram cp_X - cp_X_rm[[k]] is X' diag(mis_k) X (:25-32, src/coreLoop.cpp:120,132), so with a
+ * residual kept at zero in the missing rows, r_k = mis_k o (y_k - X beta_k):
+ *   cp_Y_X(k,j) - cp_betaX_X_jk = x_j' r_k + beta_jk * X_norm_sq(j,k),   X_norm_sq = crossprod(X^2, mis) (:23)
+ *   r_k -= delta * (mis_k o x_j).
+ * sig2_beta_vb is p x q here (update_sig2_beta_vb_, R/update_vb.R:47); cst has no log(sig2_beta) term (:108), which
+ * moves into the exponent (:129). */
+void oracle_sweep_primal_mis(int n, int p, int q, const double* X, const double* mis, const double* xnsq,
+                             double* R, double* gam_vb, const double* log_Phi, const double* log_1_min_Phi,
+                             double log_sig2_inv_vb, const double* log_tau_vb, double* m1_beta,
+                             double* mu_beta_vb, const double* sig2_beta_vb, const double* tau_vb,
+                             const int* perm, int n_ind, double c) {
+  for (int k = 0; k < q; ++k) {
+    double cst = -(log_tau_vb[k] + log_sig2_inv_vb) / 2;            /* :108 */
+    double* r = R + (size_t)k * n;
+    const double* m = mis + (size_t)k * n;
+    for (int b = 0; b < n_ind; ++b) {
+      int j = perm[b];
+      size_t jk = (size_t)j + (size_t)k * p;
+      const double* x = X + (size_t)j * n;
+      double dot = 0;
+      for (int i = 0; i < n; ++i) dot += x[i] * r[i];
+      double m1_old = m1_beta[jk];
+      double s = dot + m1_old * xnsq[jk];                            /* :120, :125 */
+      double s2 = sig2_beta_vb[jk];
+      double mu = c * s2 * tau_vb[k] * s;                            /* :125 */
+      double gam = exp(-log_one_plus_exp(c * (log_1_min_Phi[jk] - log_Phi[jk] - mu * mu / (2 * s2) -
+                                              log(s2) / 2 + cst)));  /* :127-129 */
+      mu_beta_vb[jk] = mu;
+      gam_vb[jk] = gam;
+      double m1_new = gam * mu;                                      /* :131 */
+      m1_beta[jk] = m1_new;
+      double delta = m1_new - m1_old;
+      for (int i = 0; i < n; ++i) r[i] -= delta * x[i] * m[i];       /* :132 */
+    }
+  }
+}

@@ -119,6 +119,20 @@ def sweep_primal_blocked(X, R, gam_vb, log_Phi, log_1_min_Phi, log_sig2_inv_vb, 
        ctypes.c_double(c))
 
 
+def sweep_primal_mis(X, mis, xnsq, R, gam_vb, log_Phi, log_1_min_Phi, log_sig2_inv_vb, log_tau_vb, m1_beta,
+                     mu_beta_vb, sig2_beta_vb, tau_vb, shuffled_ind, c=1.0):
+    """coreDualMisLoop in sample space: mis n x q (1 observed / 0 missing), xnsq = crossprod(X^2, mis) and
+    sig2_beta_vb p x q, R = mis * (Y - X beta) in / out."""
+    n, p = X.shape
+    q = R.shape[1]
+    fn = lib().oracle_sweep_primal_mis
+    fn.restype = None
+    fn(ctypes.c_int(n), ctypes.c_int(p), ctypes.c_int(q), _d(X), _d(mis), _d(xnsq), _d(R), _d(gam_vb),
+       _d(log_Phi), _d(log_1_min_Phi), ctypes.c_double(log_sig2_inv_vb), _d(log_tau_vb), _d(m1_beta),
+       _d(mu_beta_vb), _d(sig2_beta_vb), _d(tau_vb), _i(shuffled_ind), ctypes.c_int(len(shuffled_ind)),
+       ctypes.c_double(c))
+
+
 def residual(X, Y, beta):
     n, p = X.shape
     q = Y.shape[1]

@@ -93,10 +93,13 @@ def gsl_gamma_inc(a, x):
 
 # ----------------------------------------------------------------------------- R/update_vb.R
 def update_m2_beta_(gam_vb, mu_beta_vb, sig2_beta_vb):
-    return (mu_beta_vb ** 2 + sig2_beta_vb[None, :]) * gam_vb  # :19-31
+    s2 = sig2_beta_vb[None, :] if np.ndim(sig2_beta_vb) == 1 else sig2_beta_vb  # p x q with missing responses
+    return (mu_beta_vb ** 2 + s2) * gam_vb  # :19-31
 
 
-def update_sig2_beta_vb_(n, sig2_inv_vb, tau_vb, c=1.0):
+def update_sig2_beta_vb_(n, sig2_inv_vb, tau_vb, c=1.0, X_norm_sq=None):
+    if X_norm_sq is not None:
+        return 1 / (c * (X_norm_sq + sig2_inv_vb) * tau_vb[None, :])  # :47 (missing responses: p x q)
     return 1 / (c * (n - 1 + sig2_inv_vb) * tau_vb)  # :33-50
 
 
@@ -142,6 +145,13 @@ def update_kappa_vb_primal_(n, resid_sq, kappa, colsums_beta2, colsums_m2, sig2_
     return c * (kappa + (resid_sq + (n - 1 + sig2_inv_vb) * colsums_m2 - (n - 1) * colsums_beta2) / 2)
 
 
+def update_kappa_vb_primal_mis_(resid_sq, kappa, X_norm_sq, beta_vb, m2_beta, sig2_inv_vb, c=1.0):
+    """R/update_vb.R:149-154 (missing responses) in sample space: resid_sq is the squared norm of the masked residual,
+    which equals Y_norm_sq - 2 colSums(beta * t(cp_Y_X)) + colSums(cp_X_Xbeta * beta) with the per-trait Gram."""
+    return c * (kappa + (resid_sq + sig2_inv_vb * np.sum(m2_beta, axis=0) + np.sum(X_norm_sq * m2_beta, axis=0)
+                         - np.sum(X_norm_sq * beta_vb ** 2, axis=0)) / 2)
+
+
 def update_log_tau_vb_(eta_vb, kappa_vb):
     return sp.digamma(eta_vb) - np.log(kappa_vb)  # :159
 
@@ -172,7 +182,8 @@ def e_beta_gamma_(gam_vb, log_1_pnorm, log_pnorm, log_sig2_inv_vb, log_tau_vb, m
            - m2_beta * tau_vb[None, :] * sig2_inv_vb / 2 + gam_vb * log_pnorm
            + (1 - gam_vb) * log_1_pnorm - sig2_zeta_vb / 2 - gam_vb * np.log(gam_vb + eps)
            - (1 - gam_vb) * np.log(1 - gam_vb + eps) - sig2_theta_vb[:, None] / 2)
-    return float(np.sum(arg + 0.5 * gam_vb * (np.log(sig2_beta_vb) + 1)[None, :]))
+    ls2 = (np.log(sig2_beta_vb) + 1)[None, :] if np.ndim(sig2_beta_vb) == 1 else np.log(sig2_beta_vb) + 1  # :28-33
+    return float(np.sum(arg + 0.5 * gam_vb * ls2))
 
 
 def e_sig2_inv_(nu, nu_vb, log_sig2_inv_vb, rho, rho_vb, sig2_inv_vb):
@@ -200,6 +211,7 @@ def e_theta_hs_(lam2_inv_vb, L_vb, log_sig02_inv_vb, m0, theta_vb, Q_app, sig02_
 
 
 def e_y_(n, kappa, kappa_vb, log_tau_vb, colsums_m2, sig2_inv_vb, tau_vb):
+    """n: scalar, or colSums(mis_pat) with missing responses (:140-142 -- the same expression)."""
     arg = -n / 2 * np.log(2 * np.pi) + n / 2 * log_tau_vb
     return float(np.sum(arg - tau_vb * (kappa_vb - colsums_m2 * sig2_inv_vb / 2 - kappa)))  # :135-146
 
@@ -226,6 +238,15 @@ class _SweepState:
         else:
             self.xnorm2 = np.asfortranarray(np.sum(X ** 2, axis=0))
             self.R = native.residual(X, Y, beta_vb)
+        self.mis = None
+
+    def set_missing(self, mis_pat):
+        """R/atlasqtl_global_local_core.R:19-33 in sample space: masked residual, X_norm_sq = crossprod(X^2, mis_pat)."""
+        self.form = "primal_mis"
+        self.mis = np.asfortranarray(mis_pat)
+        self.X_norm_sq = np.asfortranarray((self.X ** 2).T @ self.mis)
+        self.n_obs = self.mis.sum(axis=0)
+        self.R = np.asfortranarray(self.R * self.mis)
 
 
 def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, list_hyper, list_init,
@@ -243,6 +264,11 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, list_
     X = np.asfortranarray(X, dtype=np.float64)
     n, q = Y.shape
     p = X.shape[1]
+    mis_pat = None
+    if np.isnan(Y).any():  # :19-33
+        mis_pat = np.where(np.isnan(Y), 0.0, 1.0)
+        Y = np.asfortranarray(np.where(np.isnan(Y), 0.0, Y))
+        sweep = "primal"
     h = list_hyper
     eta, kappa, n0, nu, rho, t02 = (np.asarray(h["eta"], float), np.asarray(h["kappa"], float),
                                     np.asarray(h["n0"], float), float(h["nu"]), float(h["rho"]),
@@ -290,6 +316,9 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, list_
     beta_vb = np.asfortranarray(gam_vb * mu_beta_vb)  # :112
     m2_beta = update_m2_beta_(gam_vb, mu_beta_vb, sig2_beta_vb)  # :113
     st = _SweepState(X, Y, beta_vb, sweep)
+    if mis_pat is not None:
+        st.set_missing(mis_pat)
+    n_eff = n if mis_pat is None else st.n_obs  # update_eta_vb_ / e_y_ use colSums(mis_pat) (R/update_vb.R:131, R/elbo.R:141)
     nu_xi_inv_vb = 1.0  # :119
 
     converged = False
@@ -308,15 +337,19 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, list_
         rho_vb = update_rho_vb_(rho, colsums_m2, tau_vb, c=c)  # :135 (OLD tau)
         sig2_inv_vb = nu_vb / rho_vb  # :137
 
-        eta_vb = update_eta_vb_(n, eta, np.sum(gam_vb, axis=0), c=c)  # :141
-        if st.form in ("reference", "dual"):
+        eta_vb = update_eta_vb_(n_eff, eta, np.sum(gam_vb, axis=0), c=c)  # :141
+        if st.form == "primal_mis":
+            kappa_vb = update_kappa_vb_primal_mis_(np.sum(st.R ** 2, axis=0), kappa, st.X_norm_sq, beta_vb, m2_beta,
+                                                   sig2_inv_vb, c=c)
+        elif st.form in ("reference", "dual"):
             kappa_vb = update_kappa_vb_dual_(n, st.Y_norm_sq, st.cp_Y_X, st.cp_X_Xbeta, kappa, beta_vb,
                                              m2_beta, sig2_inv_vb, c=c)  # :142
         else:
             kappa_vb = update_kappa_vb_primal_(n, np.sum(st.R ** 2, axis=0), kappa,
                                                np.sum(beta_vb ** 2, axis=0), colsums_m2, sig2_inv_vb, c=c)
         tau_vb = eta_vb / kappa_vb  # :145
-        sig2_beta_vb = update_sig2_beta_vb_(n, sig2_inv_vb, tau_vb, c=c)  # :147
+        sig2_beta_vb = update_sig2_beta_vb_(n, sig2_inv_vb, tau_vb, c=c,
+                                            X_norm_sq=st.X_norm_sq if st.form == "primal_mis" else None)  # :147
         log_tau_vb = update_log_tau_vb_(eta_vb, kappa_vb)  # :149
         log_sig2_inv_vb = float(update_log_sig2_inv_vb_(nu_vb, rho_vb))  # :150
 
@@ -329,6 +362,10 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, list_
                                   log_tau_vb, beta_vb, st.cp_X_Xbeta, mu_beta_vb, sig2_beta_vb, tau_vb,
                                   shuffled_ind, sample_q, c=c,
                                   impl="reference" if st.form == "reference" else "oracle")
+        elif st.form == "primal_mis":  # coreDualMisLoop (:172-175)
+            native.sweep_primal_mis(st.X, st.mis, st.X_norm_sq, st.R, gam_vb, log_Phi, log_1_min_Phi, log_sig2_inv_vb,
+                                    log_tau_vb, beta_vb, mu_beta_vb, np.asfortranarray(sig2_beta_vb), tau_vb,
+                                    shuffled_ind, c=c)
         elif st.form == "primal":
             native.sweep_primal(st.X, st.xnorm2, st.R, gam_vb, log_Phi, log_1_min_Phi, log_sig2_inv_vb,
                                 log_tau_vb, beta_vb, mu_beta_vb, sig2_beta_vb, tau_vb, shuffled_ind,
@@ -414,8 +451,13 @@ def elbo_global_local_(n, p, A2_inv, df, eta, gam_vb, kappa, L_vb, lam2_inv_vb, 
                        t02_inv, tau_vb, theta_vb, vec_sum_log_det_zeta, xi_inv_vb, zeta_vb, st, beta_vb):
     """R/atlasqtl_global_local_core.R:440-495 (c = 1 re-derivations :456-467)."""
     colsums_m2 = np.sum(m2_beta, axis=0)
+    if st.form == "primal_mis":
+        n = st.n_obs
     eta_vb = update_eta_vb_(n, eta, np.sum(gam_vb, axis=0))
-    if st.form in ("reference", "dual"):
+    if st.form == "primal_mis":
+        kappa_vb = update_kappa_vb_primal_mis_(np.sum(st.R ** 2, axis=0), kappa, st.X_norm_sq, beta_vb, m2_beta,
+                                               sig2_inv_vb)
+    elif st.form in ("reference", "dual"):
         kappa_vb = update_kappa_vb_dual_(n, st.Y_norm_sq, st.cp_Y_X, st.cp_X_Xbeta, kappa, beta_vb, m2_beta,
                                          sig2_inv_vb)
     else:

@@ -76,6 +76,37 @@ class OracleSweepContext:
         out["colsum_zpart"] = (self.gam * self.W + self.I0).sum(axis=0)
         return out
 
+    # ---- missing responses: same contract as SweepContext.set_missing / set_state_mis / sweep_mis
+    def set_missing(self, mis_pat):
+        self.mis = np.asfortranarray(mis_pat, dtype=np.float64)
+        self.Y = np.asfortranarray(self.Y * self.mis)
+        self.xnsq = np.asfortranarray((self.X ** 2).T @ self.mis)
+        return self.mis.sum(axis=0)
+
+    def set_state_mis(self, gam_vb, mu_beta_vb):
+        self.gam = np.array(gam_vb, dtype=np.float64, order="F")
+        self.mu = np.array(mu_beta_vb, dtype=np.float64, order="F")
+        self.beta = np.asfortranarray(self.gam * self.mu)
+        self.R = np.asfortranarray(self.mis * (self.Y - self.X @ self.beta))
+        out = self._sums()
+        out.update(colsum_xn_gam=(self.xnsq * self.gam).sum(axis=0),
+                   colsum_xn_gam_mu2=(self.xnsq * self.gam * self.mu ** 2).sum(axis=0),
+                   colsum_xn_beta2=(self.xnsq * self.beta ** 2).sum(axis=0))
+        return out
+
+    def sweep_mis(self, c, log_sig2_inv_vb, sig2_inv_vb, tau_vb, log_tau_vb):
+        tau = np.ascontiguousarray(tau_vb, dtype=np.float64)
+        s2 = np.asfortranarray(1.0 / (c * (self.xnsq + sig2_inv_vb) * tau[None, :]))
+        native.sweep_primal_mis(self.X, self.mis, self.xnsq, self.R, self.gam, self.log_Phi, self.log_1_min_Phi,
+                                float(log_sig2_inv_vb), np.ascontiguousarray(log_tau_vb), self.beta, self.mu, s2, tau,
+                                self.order, c=c)
+        self.launches += 1
+        g, m, xn = self.gam, self.mu, self.xnsq
+        return dict(colsum_gam=g.sum(axis=0), colsum_gam_mu2=(g * m ** 2).sum(axis=0), colsum_sig2b_gam=(s2 * g).sum(axis=0),
+                    colsum_xn_gam_mu2=(xn * g * m ** 2).sum(axis=0), colsum_xn_sig2b_gam=(xn * s2 * g).sum(axis=0),
+                    colsum_xn_beta2=(xn * (g * m) ** 2).sum(axis=0), resid_sq=(self.R ** 2).sum(axis=0),
+                    colsum_zpart=(g * self.W + self.I0).sum(axis=0), colsum_gam_logsig2b=(g * np.log(s2)).sum(axis=0))
+
     def rowsums_zpart(self):
         return (self.gam * self.W + self.I0).sum(axis=1)
 

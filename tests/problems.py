@@ -36,3 +36,19 @@ def sweep_inputs(X, Y, init, c=1.0, seed=7):
     log_1_min_Phi = np.asfortranarray(sp.log_ndtr(-u))
     return dict(gam=gam, mu=mu, theta=theta, zeta=zeta, tau=tau, sig2_beta=sig2_beta, log_tau=log_tau,
                 log_sig2_inv=log_sig2_inv, log_Phi=log_Phi, log_1_min_Phi=log_1_min_Phi, c=c)
+
+
+def mis_inputs(X, Y, si, frac=0.08, seed=11):
+    """Missing-response version of `sweep_inputs` (what R/atlasqtl_global_local_core.R:19-33, :147 hand to
+    coreDualMisLoop): mis n x q (1 observed / 0 missing; some traits fully observed), Y zeroed where missing,
+    X_norm_sq = crossprod(X^2, mis) and the p x q sig2_beta_vb of update_sig2_beta_vb_ (R/update_vb.R:47)."""
+    rng = np.random.default_rng(seed)
+    n, q = Y.shape
+    mis = (rng.uniform(size=(n, q)) >= frac).astype(np.float64)
+    mis[:, ::3] = 1.0
+    mis = np.asfortranarray(mis)
+    Ym = np.asfortranarray(Y * mis)
+    xnsq = np.asfortranarray((X ** 2).T @ mis)
+    sig2_inv = 0.7
+    sig2_beta = np.asfortranarray(1.0 / (si["c"] * (xnsq + sig2_inv) * si["tau"][None, :]))
+    return dict(mis=mis, Y=Ym, xnsq=xnsq, sig2_inv=sig2_inv, sig2_beta=sig2_beta)

@@ -48,7 +48,25 @@ def test_rejects_what_this_build_does_not_cover():
     X, Y, hyper, init = make_problem(50, 20, 5)
     with pytest.raises(ValueError):
         core.atlasqtl_global_local_core_(Y, X, 5, None, 1, 0.1, 5, 0, hyper, init, batch="0")
-    Yn = Y.copy()
-    Yn[0, 0] = np.nan
     with pytest.raises(NotImplementedError):
-        core.atlasqtl_global_local_core_(Yn, X, 5, None, 1, 0.1, 5, 0, hyper, init)
+        core.atlasqtl_global_local_core_(Y, X, 5, None, 1, 0.1, 5, 0, hyper, init, checkpoint_path="/tmp/x")
+
+
+@pytest.mark.parametrize("anneal", [None, (1, 2, 5)])
+def test_host_loop_with_missing_responses_matches_restated_r_loop(oracle_built, anneal):
+    """NaN responses: the host loop written against the per-trait sums of aq_set_state_mis / aq_sweep_mis
+    (R/update_vb.R:131, :149-154, R/elbo.R:28-30, :141) reproduces the restated R loop with mis_pat / X_norm_sq."""
+    X, Y, hyper, init = make_problem(100, 75, 20, p_act=10, q_act=20, maf=0.2, p0=(5, 25))
+    q = Y.shape[1]
+    Ym = Y.copy()
+    Ym[np.random.default_rng(3).uniform(size=Y.shape) < 0.06] = np.nan
+    tr_o, tr_c = [], []
+    ref = vb_oracle.atlasqtl_global_local_core_(Ym, X, q, anneal, 1, 0.1, 1000, hyper, init, trace=tr_o)
+    out = core.atlasqtl_global_local_core_(Ym, X, q, anneal, 1, 0.1, 1000, 0, hyper, init, debug=True,
+                                           context_factory=lambda X_, Y_: OracleSweepContext(X_, Y_), trace=tr_c)
+    assert ref["converged"] and out["converged"] and out["it"] == ref["it"]
+    for a, b in zip(tr_o, tr_c):
+        assert (a["lb"] is None) == (b["lb"] is None)
+        if a["lb"] is not None:
+            assert abs(a["lb"] - b["lb"]) <= 1e-10 * abs(a["lb"])
+    assert np.abs(out["gam_vb"] - ref["gam_vb"]).max() <= 1e-10

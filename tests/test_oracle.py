@@ -116,3 +116,41 @@ def test_q_approx_vec_and_bfdr():
     ppi = np.array([[0.9, 0.2], [0.99, 0.6]])
     fdr = vb_oracle.assign_bFDR(ppi)
     np.testing.assert_allclose(fdr, [[(0.01 + 0.1) / 2, (0.01 + 0.1 + 0.4 + 0.8) / 4], [0.01, (0.01 + 0.1 + 0.4) / 3]])
+
+
+def test_masked_primal_sweep_matches_reference_mis_loop(oracle_built):
+    """coreDualMisLoop (src/coreLoop.cpp:91-138) with the per-trait Gram corrections cp_X_rm of
+    R/atlasqtl_global_local_core.R:25-32, against the sample-space restatement with a masked residual."""
+    from problems import mis_inputs
+    native = oracle_built
+    if not native.ref_available():
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    X, Y, hyper, init = make_problem(60, 40, 12)
+    p, q = X.shape[1], Y.shape[1]
+    si = sweep_inputs(X, Y, init, c=0.7)
+    mi = mis_inputs(X, Y, si)
+    order = np.random.default_rng(2).permutation(p).astype(np.int32)
+    # the reference's inputs
+    cp_X = np.asfortranarray(X.T @ X)
+    cp_X_rm = np.zeros((p, p, q), order="F")
+    for k in range(q):
+        rows = np.flatnonzero(mi["mis"][:, k] == 0)
+        cp_X_rm[:, :, k] = X[rows].T @ X[rows]
+    cp_Y_X = np.asfortranarray(mi["Y"].T @ X)
+    gam_r, mu_r = si["gam"].copy(order="F"), si["mu"].copy(order="F")
+    beta_r = np.asfortranarray(gam_r * mu_r)
+    cbx = np.asfortranarray(cp_X @ beta_r - np.stack([cp_X_rm[:, :, k] @ beta_r[:, k] for k in range(q)], axis=1))
+    native.ref_core_dual_mis_loop(cp_X, cp_X_rm, cp_Y_X, gam_r, si["log_Phi"], si["log_1_min_Phi"], si["log_sig2_inv"],
+                                  si["log_tau"], beta_r, cbx, mu_r, mi["sig2_beta"], si["tau"], order,
+                                  np.arange(q, dtype=np.int32), c=0.7)
+    # ours
+    gam, mu = si["gam"].copy(order="F"), si["mu"].copy(order="F")
+    beta = np.asfortranarray(gam * mu)
+    R = np.asfortranarray(mi["mis"] * (mi["Y"] - X @ beta))
+    native.sweep_primal_mis(X, mi["mis"], mi["xnsq"], R, gam, si["log_Phi"], si["log_1_min_Phi"], si["log_sig2_inv"],
+                            si["log_tau"], beta, mu, mi["sig2_beta"], si["tau"], order, c=0.7)
+    assert np.abs(gam - gam_r).max() <= 1e-12
+    assert np.abs(mu - mu_r).max() <= 1e-12
+    assert np.abs(beta - beta_r).max() <= 1e-12
+    # the reference's running X'(mis o X) beta equals X'(mis o Y - R)
+    np.testing.assert_allclose(X.T @ (mi["Y"] - R), cbx, atol=1e-9)
