@@ -18,6 +18,21 @@
 #   :472     e_beta_gamma_(...)         ->  sum(s$colsum_gam * (log_sig2_inv_vb/2 + log_tau_vb/2 + (log(sig2_beta_vb)+1)/2)) -
 #                                           sum(colsum_m2 * tau_vb) * sig2_inv_vb/2 + elbo_B_dev - p*q*sig2_zeta_vb/2 - q*sum(sig2_theta_vb)/2
 #   :418-428 output                     ->  gam_vb <- beta_vb <- matrix(0, p, q); .Call(`_atlasqtl_aq_get_state`, ctx, gam_vb, NULL, beta_vb)
+#
+# Missing responses (any(is.na(Y)), :19-38 and the mis_pat branches of R/update_vb.R / R/elbo.R):
+#   :21-33   mis_pat, X_norm_sq, cp_X_rm  ->  mis_pat <- ifelse(is.na(Y), 0, 1); Y[is.na(Y)] <- 0
+#                                             n_obs <- .Call(`_atlasqtl_aq_set_missing`, ctx, mis_pat)      # = colSums(mis_pat)
+#   :112-115 (m2_beta with sweep = TRUE)   ->  s <- .Call(`_atlasqtl_aq_set_state_mis`, ctx, gam_vb, mu_beta_vb)
+#                                             colsum_m2 <- s$colsum_gam_mu2 + sig2_beta_vb * s$colsum_gam
+#                                             colsum_xn_m2 <- s$colsum_xn_gam_mu2 + sig2_beta_vb * s$colsum_xn_gam
+#   :141     update_eta_vb_(.., mis_pat)   ->  c * (eta + n_obs/2 + s$colsum_gam/2) - c + 1
+#   :142     update_kappa_vb_(.., X_norm_sq) -> c * (kappa + (s$resid_sq + sig2_inv_vb * colsum_m2 + colsum_xn_m2 - s$colsum_xn_beta2)/2)
+#   :147     update_sig2_beta_vb_(.., X_norm_sq) -> formed on the device inside the sweep (p x q never exists in R)
+#   :172-175 coreDualMisLoop(...)          ->  s <- .Call(`_atlasqtl_aq_sweep_mis`, ctx, c, log_sig2_inv_vb, sig2_inv_vb, tau_vb, log_tau_vb)
+#   :235     m2_beta (p x q sig2_beta_vb)  ->  colsum_m2 <- s$colsum_gam_mu2 + s$colsum_sig2b_gam
+#                                             colsum_xn_m2 <- s$colsum_xn_gam_mu2 + s$colsum_xn_sig2b_gam
+#   :470     e_y_(.., mis_pat)             ->  arg <- n_obs * (log_tau_vb - log(2 * pi)) / 2
+#   :472     e_beta_gamma_ (p x q sig2_beta_vb) -> sum(s$colsum_gam * (log_sig2_inv_vb/2 + log_tau_vb/2 + 1/2) + s$colsum_gam_logsig2b/2) - ...
 
 coreDualLoop <- function(cp_X, cp_Y_X, gam_vb, log_Phi_theta_plus_zeta, log_1_min_Phi_theta_plus_zeta,
                          log_sig2_inv_vb, log_tau_vb, m1_beta, cp_betaX_X, mu_beta_vb, sig2_beta_vb, tau_vb,

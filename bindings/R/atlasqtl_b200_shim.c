@@ -105,6 +105,51 @@ SEXP _atlasqtl_aq_rowsums_zpart(SEXP ptr, SEXP p) {
   return v;
 }
 
+/* ---- missing responses: replaces `_atlasqtl_coreDualMisLoop` (src/RcppExports.cpp:41-63) and its set-up
+ * (X_norm_sq, cp_X_rm; R/atlasqtl_global_local_core.R:19-33) */
+static SEXP named_qvecs(int q, const char** names, int k, double** out) {
+  SEXP res = PROTECT(Rf_allocVector(VECSXP, k)), nm = PROTECT(Rf_allocVector(STRSXP, k));
+  for (int i = 0; i < k; ++i) {
+    SEXP v = PROTECT(Rf_allocVector(REALSXP, q));
+    out[i] = REAL(v);
+    SET_VECTOR_ELT(res, i, v);
+    SET_STRING_ELT(nm, i, Rf_mkChar(names[i]));
+    UNPROTECT(1);
+  }
+  Rf_setAttrib(res, R_NamesSymbol, nm);
+  UNPROTECT(2);
+  return res;
+}
+
+/* mis_pat: the n x q double matrix ifelse(is.na(Y), 0, 1); returns colSums(mis_pat) */
+SEXP _atlasqtl_aq_set_missing(SEXP ptr, SEXP mis_pat) {
+  SEXP n_obs = PROTECT(Rf_allocVector(REALSXP, Rf_ncols(mis_pat)));
+  check(aq_set_missing(get_ctx(ptr), REAL(mis_pat), REAL(n_obs)));
+  UNPROTECT(1);
+  return n_obs;
+}
+
+SEXP _atlasqtl_aq_set_state_mis(SEXP ptr, SEXP gam_vb, SEXP mu_beta_vb) {
+  static const char* names[] = {"colsum_gam", "colsum_gam_mu2", "colsum_beta2", "resid_sq", "colsum_xn_gam",
+                                "colsum_xn_gam_mu2", "colsum_xn_beta2"};
+  double* o[7];
+  SEXP res = PROTECT(named_qvecs(Rf_ncols(gam_vb), names, 7, o));
+  check(aq_set_state_mis(get_ctx(ptr), REAL(gam_vb), REAL(mu_beta_vb), o[0], o[1], o[2], o[3], o[4], o[5], o[6]));
+  UNPROTECT(1);
+  return res;
+}
+
+SEXP _atlasqtl_aq_sweep_mis(SEXP ptr, SEXP c, SEXP log_sig2_inv_vb, SEXP sig2_inv_vb, SEXP tau_vb, SEXP log_tau_vb) {
+  static const char* names[] = {"colsum_gam", "colsum_gam_mu2", "colsum_sig2b_gam", "colsum_xn_gam_mu2",
+                                "colsum_xn_sig2b_gam", "colsum_xn_beta2", "resid_sq", "colsum_zpart", "colsum_gam_logsig2b"};
+  double* o[9];
+  SEXP res = PROTECT(named_qvecs(Rf_length(tau_vb), names, 9, o));
+  check(aq_sweep_mis(get_ctx(ptr), Rf_asReal(c), Rf_asReal(log_sig2_inv_vb), Rf_asReal(sig2_inv_vb), REAL(tau_vb),
+                     REAL(log_tau_vb), o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8]));
+  UNPROTECT(1);
+  return res;
+}
+
 /* Stateless drop-in with the reference's exact 15 arguments (src/RcppExports.cpp:17). */
 SEXP _atlasqtl_coreDualLoop(SEXP cp_X, SEXP cp_Y_X, SEXP gam_vb, SEXP log_Phi, SEXP log_1_min_Phi, SEXP log_sig2_inv_vb,
                             SEXP log_tau_vb, SEXP m1_beta, SEXP cp_betaX_X, SEXP mu_beta_vb, SEXP sig2_beta_vb,
@@ -126,6 +171,9 @@ static const R_CallMethodDef CallEntries[] = {
     {"_atlasqtl_aq_refresh_tables", (DL_FUNC)&_atlasqtl_aq_refresh_tables, 5},
     {"_atlasqtl_aq_sweep", (DL_FUNC)&_atlasqtl_aq_sweep, 6},
     {"_atlasqtl_aq_rowsums_zpart", (DL_FUNC)&_atlasqtl_aq_rowsums_zpart, 2},
+    {"_atlasqtl_aq_set_missing", (DL_FUNC)&_atlasqtl_aq_set_missing, 2},
+    {"_atlasqtl_aq_set_state_mis", (DL_FUNC)&_atlasqtl_aq_set_state_mis, 3},
+    {"_atlasqtl_aq_sweep_mis", (DL_FUNC)&_atlasqtl_aq_sweep_mis, 6},
     {"_atlasqtl_coreDualLoop", (DL_FUNC)&_atlasqtl_coreDualLoop, 15},
     {NULL, NULL, 0}};
 
