@@ -12,6 +12,7 @@
 #include "../../include/atlasqtl_b200.h"
 #include "aq_internal.h"
 #include "aq_mis.cuh"
+#include "aq_select.cuh"
 #include "aq_stream.cuh"
 #include "aq_sweep.cuh"
 
@@ -106,6 +107,7 @@ struct aq_ctx {
     unsigned long long* mask = nullptr;
     double *xnsq = nullptr, *n_obs = nullptr, *mis_out = nullptr;
     bool has_mis = false;
+    double* sel_partial = nullptr;  // scratch of the selection kernels: 2 x kSelBlocks partials + 2 results
     std::vector<int32_t> order, order_pad;
     std::vector<double> hbuf;   // pinned-size-agnostic host scratch
     bool have_state = false, have_tables = false;
@@ -360,7 +362,7 @@ int aq_destroy(aq_ctx* c) {
         if (b) cudaFree(b);
     if (c->order_dev) cudaFree(c->order_dev);
     if (c->mask) cudaFree(c->mask);
-    for (double* b : {c->xnsq, c->n_obs, c->mis_out})
+    for (double* b : {c->xnsq, c->n_obs, c->mis_out, c->sel_partial})
         if (b) cudaFree(b);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -730,6 +732,86 @@ int aq_sweep_mis(aq_ctx* c, double cc, double log_sig2_inv_vb, double sig2_inv_v
     rc = fetch_mis(c, rows, outs, 9);
     if (rc != AQ_OK) return rc;
     AQ_CUDA(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+    return AQ_OK;
+}
+
+// ---------------------------------------------------------------- selection sets (R/summarise_output.R:99-106, :207-223)
+namespace {
+int sel_scratch(aq_ctx* c) {
+    if (!c->have_state) return fail(AQ_ESTATE, "selection before aq_set_state");
+    AQ_CUDA(cudaSetDevice(c->device));
+    if (!c->sel_partial) AQ_CUDA(cudaMalloc((void**)&c->sel_partial, sizeof(double) * (2 * kSelBlocks + 2)));
+    return AQ_OK;
+}
+}  // namespace
+
+int aq_ppi_count_sum(aq_ctx* c, double t, double* count, double* sum) {
+    if (!c || !count || !sum) return fail(AQ_EINVAL, "aq_ppi_count_sum: NULL argument");
+    int rc = sel_scratch(c);
+    if (rc != AQ_OK) return rc;
+    double* res = c->sel_partial + 2 * kSelBlocks;
+    ppi_count_sum_kernel<<<kSelBlocks, 256, 0, c->stream>>>(c->gam, c->p, c->q, c->q_pad, t, c->sel_partial);
+    ppi_finish_kernel<<<1, 256, 0, c->stream>>>(c->sel_partial, kSelBlocks, 0, res);
+    AQ_CUDA(cudaGetLastError());
+    c->launches += 2;
+    double h[2];
+    AQ_CUDA(cudaMemcpyAsync(h, res, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    AQ_CUDA(cudaStreamSynchronize(c->stream));
+    *count = h[0];
+    *sum = h[1];
+    return AQ_OK;
+}
+
+int aq_ppi_next_above(aq_ctx* c, double t, double* next) {
+    if (!c || !next) return fail(AQ_EINVAL, "aq_ppi_next_above: NULL argument");
+    int rc = sel_scratch(c);
+    if (rc != AQ_OK) return rc;
+    double* res = c->sel_partial + 2 * kSelBlocks;
+    ppi_next_kernel<<<kSelBlocks, 256, 0, c->stream>>>(c->gam, c->p, c->q, c->q_pad, t, c->sel_partial);
+    ppi_finish_kernel<<<1, 256, 0, c->stream>>>(c->sel_partial, kSelBlocks, 1, res);
+    AQ_CUDA(cudaGetLastError());
+    c->launches += 2;
+    AQ_CUDA(cudaMemcpyAsync(next, res, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    AQ_CUDA(cudaStreamSynchronize(c->stream));
+    return AQ_OK;
+}
+
+int aq_ppi_collect(aq_ctx* c, int mode, double lo, double hi, int64_t capacity, int32_t* out_j, int32_t* out_k,
+                   double* out_gam, int64_t* n_found) {
+    if (!c || !n_found) return fail(AQ_EINVAL, "aq_ppi_collect: NULL argument");
+    if (mode != 0 && mode != 1) return fail(AQ_EINVAL, "aq_ppi_collect: mode must be 0 (1 - PPI in (lo, hi]) or 1 (PPI > lo)");
+    if (capacity < 0 || (capacity > 0 && (!out_j || !out_k || !out_gam))) return fail(AQ_EINVAL, "aq_ppi_collect: bad output buffers");
+    int rc = sel_scratch(c);
+    if (rc != AQ_OK) return rc;
+    int *dj = nullptr, *dk = nullptr;
+    double* dg = nullptr;
+    unsigned long long* cnt = reinterpret_cast<unsigned long long*>(c->sel_partial);
+    const size_t cap = (size_t)std::max<int64_t>(capacity, 1);
+    cudaError_t e = cudaMalloc((void**)&dj, sizeof(int) * cap);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dk, sizeof(int) * cap);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dg, sizeof(double) * cap);
+    if (e == cudaSuccess) e = cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream);
+    unsigned long long found = 0;
+    if (e == cudaSuccess) {
+        ppi_collect_kernel<<<kSelBlocks, 256, 0, c->stream>>>(c->gam, c->p, c->q, c->q_pad, mode, lo, hi, (long long)capacity,
+                                                               dj, dk, dg, cnt);
+        e = cudaGetLastError();
+        c->launches++;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&found, cnt, sizeof(found), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    const size_t ncopy = (size_t)std::min<unsigned long long>(found, (unsigned long long)capacity);
+    if (e == cudaSuccess && ncopy) e = cudaMemcpy(out_j, dj, sizeof(int) * ncopy, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && ncopy) e = cudaMemcpy(out_k, dk, sizeof(int) * ncopy, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && ncopy) e = cudaMemcpy(out_gam, dg, sizeof(double) * ncopy, cudaMemcpyDeviceToHost);
+    cudaFree(dj);
+    cudaFree(dk);
+    cudaFree(dg);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? AQ_ENOMEM : AQ_ECUDA, std::string("aq_ppi_collect: ") + cudaGetErrorString(e));
+    }
+    *n_found = (int64_t)found;
     return AQ_OK;
 }
 

@@ -122,6 +122,30 @@ class SweepContext:
         return dict(zip(("colsum_gam", "colsum_gam_mu2", "colsum_sig2b_gam", "colsum_xn_gam_mu2", "colsum_xn_sig2b_gam",
                          "colsum_xn_beta2", "resid_sq", "colsum_zpart", "colsum_gam_logsig2b"), o))
 
+    # ---- selection sets on the device (R/summarise_output.R:99-106, :207-223)
+    def ppi_count_sum(self, t):
+        """(#{1 - gam_vb <= t}, sum of those 1 - gam_vb) over this slab."""
+        cnt, tot = ctypes.c_double(), ctypes.c_double()
+        _lib.check(self._lib.aq_ppi_count_sum(self._ctx, ctypes.c_double(t), ctypes.byref(cnt), ctypes.byref(tot)))
+        return cnt.value, tot.value
+
+    def ppi_next_above(self, t):
+        nxt = ctypes.c_double()
+        _lib.check(self._lib.aq_ppi_next_above(self._ctx, ctypes.c_double(t), ctypes.byref(nxt)))
+        return nxt.value
+
+    def ppi_collect(self, mode, lo, hi, capacity):
+        """Pairs with lo < 1 - gam_vb <= hi (mode 0) or gam_vb > lo (mode 1): (j, k_local, gam_vb, n_found), sorted by
+        column-major index."""
+        cap = int(capacity)
+        j, k, g = np.empty(max(cap, 1), np.int32), np.empty(max(cap, 1), np.int32), np.empty(max(cap, 1))
+        n = ctypes.c_int64()
+        _lib.check(self._lib.aq_ppi_collect(self._ctx, ctypes.c_int(mode), ctypes.c_double(lo), ctypes.c_double(hi),
+                                            ctypes.c_int64(cap), _lib.iptr(j), _lib.iptr(k), _lib.dptr(g), ctypes.byref(n)))
+        m = min(n.value, cap)
+        o = np.lexsort((j[:m], k[:m]))
+        return j[:m][o], k[:m][o], g[:m][o], n.value
+
     def rowsums_zpart(self):
         r = np.empty(self.p)
         _lib.check(self._lib.aq_rowsums_zpart(self._ctx, _lib.dptr(r)))

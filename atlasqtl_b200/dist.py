@@ -37,6 +37,13 @@ class TorchComm:
         self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM)
         return t.cpu().numpy()
 
+    def allreduce_min(self, x):
+        t = self._torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))
+        if self.device.type == "cuda":
+            t = t.to(self.device, non_blocking=False)
+        self._dist.all_reduce(t, op=self._dist.ReduceOp.MIN)
+        return t.cpu().numpy()
+
     def gather_result(self, res, q):
         """Assemble the full-width output object on every rank (all_gather of the p x q_local slabs)."""
         out = dict(res)

@@ -161,6 +161,21 @@ int aq_sweep_mis(aq_ctx* ctx, double c, double log_sig2_inv_vb, double sig2_inv_
                  double* colsum_xn_gam_mu2, double* colsum_xn_sig2b_gam, double* colsum_xn_beta2, double* resid_sq,
                  double* colsum_zpart, double* colsum_gam_logsig2b);
 
+/*
+ * Selection sets without downloading the p x q PPI matrix (post-processing of the path's output:
+ * `assign_bFDR` R/summarise_output.R:207-223 and the threshold sets of `summary` :99-106).  With e = 1 - gam_vb:
+ *   aq_ppi_count_sum   count = #{(j,k): e <= t}, sum = sum of those e  (over this slab; deterministic reductions)
+ *   aq_ppi_next_above  the smallest e > t (+Inf if none)
+ *   aq_ppi_collect     the pairs with  lo < e <= hi  (mode 0)  or  gam_vb > lo  (mode 1)  as (j, k_local, gam_vb) triples in
+ *                      arbitrary order; n_found is the number of matching pairs, of which min(n_found, capacity) were written
+ * The running mean of the sorted e is non-decreasing, so {bFDR < thres} is a prefix of the sorted order: a bisection on t
+ * with aq_ppi_count_sum finds it (atlasqtl_b200/summarise.py::select_bFDR_device; sums over slabs / GPUs add up).
+ */
+int aq_ppi_count_sum(aq_ctx* ctx, double t, double* count, double* sum);
+int aq_ppi_next_above(aq_ctx* ctx, double t, double* next);
+int aq_ppi_collect(aq_ctx* ctx, int mode, double lo, double hi, int64_t capacity, int32_t* out_j, int32_t* out_k,
+                   double* out_gam, int64_t* n_found);
+
 /* Count of kernel launches issued through this context so far (bench.py's gpu_launches). */
 int64_t aq_launch_count(const aq_ctx* ctx);
 

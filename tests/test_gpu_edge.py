@@ -188,3 +188,53 @@ def test_size_independent_properties_at_scale():
     np.testing.assert_allclose(out["colsum_gam"], st["gam_vb"].sum(axis=0), rtol=1e-11)
     np.testing.assert_allclose(out["colsum_beta2"], (st["beta_vb"] ** 2).sum(axis=0), rtol=1e-10, atol=1e-300)
     np.testing.assert_allclose(out["colsum_gam"], again["colsum_gam"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("thres", [0.05, 0.25, 0.6])
+def test_selection_sets_on_device_match_assign_bFDR(thres):
+    """{PPI > thres} and {bFDR < thres} formed on the device (bisection on streaming count/sum passes) are exactly the
+    sets of the reference's assign_bFDR / summary (R/summarise_output.R:99-106, :207-223), ties included."""
+    from atlasqtl_b200 import summarise
+    from atlasqtl_b200.device import SweepContext
+    rng = np.random.default_rng(12)
+    n, p, q = 40, 300, 130
+    X = np.asfortranarray(rng.normal(size=(n, p)))
+    Y = np.asfortranarray(rng.normal(size=(n, q)))
+    gam = rng.uniform(size=(p, q)) ** 6
+    hot = rng.uniform(size=(p, q)) < 0.03
+    gam[hot] = 1 - rng.uniform(size=hot.sum()) ** 3 * 0.2
+    gam[5:9, 3] = gam[11, 7] = gam[200, 100]          # exact ties
+    gam[0, 0], gam[1, 1] = 1.0, 0.0
+    gam = np.asfortranarray(gam)
+    with SweepContext(X, Y) as ctx:
+        ctx.set_state(gam, np.zeros((p, q)))
+        rows, cols = summarise.select_ppi_device(ctx, thres)
+        assert np.array_equal(np.stack([rows, cols], 1), np.argwhere(gam.T > thres)[:, ::-1])
+        rows, cols, nsel = summarise.select_bFDR_device(ctx, thres)
+    want = summarise.assign_bFDR(gam) < thres
+    got = np.zeros_like(want)
+    got[rows, cols] = True
+    assert nsel == want.sum() == len(rows)
+    assert np.array_equal(got, want)
+
+
+def test_bfdr_device_ties_at_the_boundary():
+    """All PPIs equal: the running mean is flat, so either everything or nothing is selected; and a block of ties that is
+    only partly inside the prefix is cut in column-major order."""
+    from atlasqtl_b200 import summarise
+    from atlasqtl_b200.device import SweepContext
+    rng = np.random.default_rng(1)
+    n, p, q = 30, 16, 12
+    X = np.asfortranarray(rng.normal(size=(n, p)))
+    Y = np.asfortranarray(rng.normal(size=(n, q)))
+    gam = np.full((p, q), 0.5)
+    gam[:4, 0] = 0.99
+    gam[2, 5] = gam[7, 2] = gam[9, 9] = gam[3, 1] = 0.8   # ties; with thres = 0.1 only some of them fit
+    for thres in (0.1, 0.08, 0.3, 0.6):
+        with SweepContext(X, Y) as ctx:
+            ctx.set_state(np.asfortranarray(gam), np.zeros((p, q)))
+            rows, cols, nsel = summarise.select_bFDR_device(ctx, thres)
+        want = summarise.assign_bFDR(gam) < thres
+        got = np.zeros_like(want)
+        got[rows, cols] = True
+        assert np.array_equal(got, want), thres
