@@ -30,6 +30,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the main sweep kernel, from the committed
+# `ncu --set full` capture of this very command (profiles/r1_ncu_sweep_c2_full_v4.txt): 42.54 GB + 15.28 GB for 1184 of the
+# 1250 trait tiles; the algorithmic figure is 56 B per update (read gam, mu, D, W, I0; write gam, mu) = 53 GB for them.
+NCU_TRAFFIC_BYTES = {("C2", 1): 57.82e9}
+
 FP64_PEAK_TFLOPS = 37.05  # measured DMMA m8n8k4 peak on this pool's B200 (profiles/r1_fp64_peaks_microbench.txt);
                           # MEASURED_PEAKS.json has no fp64 entry (bf16 / HBM only)
 
@@ -336,8 +341,10 @@ def main():
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(n_launch),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                         "frac": achieved / FP64_PEAK_TFLOPS, "traffic": None,
-                         "kernel": "sweep_kernel (fp64 DMMA m8n8k4)", "ms": sweep_ms,
+                         "frac": achieved / FP64_PEAK_TFLOPS,
+                         "traffic": NCU_TRAFFIC_BYTES.get((args.config, world)),
+                         "kernel": "sweep_kernel (fp64 DMMA m8n8k4): full-size tile launch + 8-trait tail launch of one sweep",
+                         "ms": sweep_ms,
                          "peak_source": "measured fp64 DMMA peak, tools/microbench/fp64_peaks.cu on this pool "
                                         "(MEASURED_PEAKS.json has no fp64 entry)",
                          "algorithmic": "4*n flops per SNPxtrait update"},
