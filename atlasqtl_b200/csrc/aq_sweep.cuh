@@ -89,7 +89,7 @@ struct SweepCfg {
     static constexpr size_t kDbufDoubles = (size_t)2 * kT * kBlk;
     static constexpr size_t kRsqDoubles = (size_t)WS * kT;
     static constexpr size_t kIoDoubles = (size_t)2 * kBlk * 2 * kT;  // [2][kBlk][2][kT]: in beta_old, c (D + cst); out gam, mu
-    static constexpr size_t kStgDoubles = (size_t)3 * kBlk * kT;     // [3][kBlk][kT]: gam, mu, D rows of the next block
+    static constexpr size_t kStgDoubles = (size_t)5 * kBlk * kT;     // [5][kBlk][kT]: gam, mu, D, W, I0 rows of the next block
     static constexpr uint32_t kDeltaBytes = (uint32_t)(kT * kBlk * sizeof(double));  // one -Delta block
     // cluster variant only: followers' reduced S tiles and squared-norm partials land in the leader's shared memory
     static constexpr size_t kRedDoubles = kCl ? (size_t)2 * (kMaxCluster - 1) * kT * kSps : 0;
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
     double* dbuf = ssum + Cfg::kSsumDoubles;              // [2][kT][kBlk]  (holds -Delta)
     double* rsqs = dbuf + Cfg::kDbufDoubles;              // [WS][kT]
     double* iobuf = rsqs + Cfg::kRsqDoubles;              // [2][kBlk][2][kT]
-    double* stg = iobuf + Cfg::kIoDoubles;                // [3][kBlk][kT]
+    double* stg = iobuf + Cfg::kIoDoubles;                // [5][kBlk][kT]
     double* red = stg + Cfg::kStgDoubles;                 // leader: [2][kMaxCluster-1][kT][kSps]
     double* rsq_all = red + Cfg::kRedDoubles;             // leader: [kMaxCluster-1][kT]
     uint64_t* bars = reinterpret_cast<uint64_t*>(rsq_all + Cfg::kRsqAllDoubles);
@@ -420,12 +420,16 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
             constexpr int kH = (kT <= 16) ? 2 : 1;
             constexpr int kTP = kBlk / kH;           // SNP slots per lane
             constexpr int kW0 = (WS + kH - 1) / kH;  // split-K partials per lane
+            // W / I0 of a block: staged with the other rows when a lane handles 4 SNP slots; with 8 slots per lane (T > 16)
+            // the extra asynchronous copies cost more than they hide, and W / I0 are requested directly one block ahead
+            constexpr bool kStageWI = (kH == 2);
             const int half = (kH == 2) ? (lane >> 4) : 0;
             const int tl = (kH == 2) ? (lane & 15) : lane;
             const bool active = tl < kT;
             const int tls = active ? tl : 0;
             const int t0 = half * kTP;
             int idn[kTP], idc[kTP];
+            double wn[kTP], in[kTP];   // W, I0 of the block being prepared: consumed after its chain
             long gb = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int tile = group + ti * ngroups;
@@ -434,7 +438,8 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 const double sig2 = P.sig2_beta[k];
                 const double cst = -(P.log_tau[k] + P.log_sig2_inv + log(sig2)) / 2;  // src/coreLoop.cpp:56
                 double sg = 0.0, sgm2 = 0.0, sb2 = 0.0, sz = 0.0;
-                // asynchronous copies (LDGSTS) of this lane's gam / mu / D elements of block `blk` into the staging buffer
+                // asynchronous copies (LDGSTS) of this lane's gam / mu / D / W / I0 elements of block `blk` into the staging
+                // buffer: issued a whole block ahead, so neither preparing a block nor finishing it ever waits on HBM or L2
                 auto stage_rows = [&](int blk) {
                     if (active) {
 #pragma unroll
@@ -445,6 +450,10 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                             cp_async8(stg + (0 * kBlk + t) * kT + tl, P.gam + off);
                             cp_async8(stg + (1 * kBlk + t) * kT + tl, P.mu + off);
                             cp_async8(stg + (2 * kBlk + t) * kT + tl, P.dtab + off);
+                            if (kStageWI) {
+                                cp_async8(stg + (3 * kBlk + t) * kT + tl, P.wtab + off);
+                                cp_async8(stg + (4 * kBlk + t) * kT + tl, P.i0tab + off);
+                            }
                         }
                     }
                     cp_async_commit();
@@ -459,6 +468,10 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                         idn[i] = __ldg(P.order + (size_t)blk * kBlk + t);
                         const double go = stg[(0 * kBlk + t) * kT + tls], mo = stg[(1 * kBlk + t) * kT + tls];
                         const double dd = stg[(2 * kBlk + t) * kT + tls];
+                        if (kStageWI) {
+                            wn[i] = stg[(3 * kBlk + t) * kT + tls];
+                            in[i] = stg[(4 * kBlk + t) * kT + tls];
+                        }
                         if (active) {
                             io[(t * 2 + 0) * kT + tl] = idn[i] >= 0 ? go * mo : 0.0;  // beta_old (0 for padding slots)
                             io[(t * 2 + 1) * kT + tl] = P.c * (dd + cst);              // :75-77 without the mu^2 term
@@ -519,22 +532,8 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     if (lane == 0) mbar_arrive(&inready[g & 1]);
                     AQ_T(7);
                 };
-                auto post = [&](long g, int pf_block, const double (&ww)[kTP], const double (&ii)[kTP]) {
+                auto post = [&](long g, const double (&ww)[kTP], const double (&ii)[kTP]) {
                     AQ_T0();
-                    // while the chain runs: pull the rows of block b + 2 (all five p x q arrays) into L2, so that the copies
-                    // and loads issued for it one block from now are L2 hits
-                    if (pf_block >= 0) {
-                        constexpr int kL = (kT * 8 > 128) ? 2 : 1;  // 128-byte lines per row segment
-                        const int* ord = P.order + (size_t)pf_block * kBlk;
-                        for (int it = lane; it < 5 * kBlk * kL; it += 32) {
-                            const int a = it / (kBlk * kL), t = (it % (kBlk * kL)) / kL, e = it % kL;
-                            const int id = __ldg(ord + t);
-                            if (id >= 0) {
-                                const double* base = a == 0 ? P.gam : a == 1 ? P.mu : a == 2 ? P.dtab : a == 3 ? P.wtab : P.i0tab;
-                                prefetch_l2(base + (size_t)id * P.q_pad + P.k_base + tile * kT + e * (kT - 1));
-                            }
-                        }
-                    }
                     mbar_wait(&dready[g & 1], (uint32_t)((g >> 1) & 1));
                     AQ_T(8);
                     const double* io = iobuf + (size_t)(g & 1) * kBlk * 2 * kT;
@@ -561,16 +560,21 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 stage_rows(0);
                 pre(gb, 0);
                 for (int b = 0; b < nb; ++b, ++gb) {
-                    double ww[kTP], ii[kTP];  // requested before the next block is prepared, consumed after the chain
+                    double ww[kTP], ii[kTP];
 #pragma unroll
                     for (int i = 0; i < kTP; ++i) {
                         idc[i] = idn[i];
-                        const size_t off = (size_t)(idc[i] < 0 ? 0 : idc[i]) * P.q_pad + k;
-                        ww[i] = P.wtab[off];
-                        ii[i] = P.i0tab[off];
+                        if (kStageWI) {
+                            ww[i] = wn[i];
+                            ii[i] = in[i];
+                        } else {  // requested before the next block is prepared, consumed after the chain
+                            const size_t off = (size_t)(idc[i] < 0 ? 0 : idc[i]) * P.q_pad + k;
+                            ww[i] = P.wtab[off];
+                            ii[i] = P.i0tab[off];
+                        }
                     }
                     if (b + 1 < nb) pre(gb + 1, b + 1);
-                    post(gb, b + 2 < nb ? b + 2 : -1, ww, ii);
+                    post(gb, ww, ii);
                 }
                 if (kH == 2) {
                     sg += __shfl_xor_sync(0xffffffffu, sg, 16);
