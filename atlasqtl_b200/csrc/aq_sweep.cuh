@@ -441,19 +441,20 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 // asynchronous copies (LDGSTS) of this lane's gam / mu / D / W / I0 elements of block `blk` into the staging
                 // buffer: issued a whole block ahead, so neither preparing a block nor finishing it ever waits on HBM or L2
                 auto stage_rows = [&](int blk) {
-                    if (active) {
+                    // 16-byte copies: a row of kT traits is kT / 2 lanes wide, so one instruction covers 64 / kT rows
+                    constexpr int kLanesPerRow = kT / 2, kRowsPerInst = 32 / kLanesPerRow;
+                    constexpr int kArrays = kStageWI ? 5 : 3;
+                    const int idr = __ldg(P.order + (size_t)blk * kBlk + (lane & 7));
+                    const int rsub = lane / kLanesPerRow, csub = 2 * (lane % kLanesPerRow);
+                    const size_t kcol = (size_t)P.k_base + (size_t)tile * kT + csub;
 #pragma unroll
-                        for (int i = 0; i < kTP; ++i) {
-                            const int t = t0 + i;
-                            const int idt = __ldg(P.order + (size_t)blk * kBlk + t);
-                            const size_t off = (size_t)(idt < 0 ? 0 : idt) * P.q_pad + k;
-                            cp_async8(stg + (0 * kBlk + t) * kT + tl, P.gam + off);
-                            cp_async8(stg + (1 * kBlk + t) * kT + tl, P.mu + off);
-                            cp_async8(stg + (2 * kBlk + t) * kT + tl, P.dtab + off);
-                            if (kStageWI) {
-                                cp_async8(stg + (3 * kBlk + t) * kT + tl, P.wtab + off);
-                                cp_async8(stg + (4 * kBlk + t) * kT + tl, P.i0tab + off);
-                            }
+                    for (int r0 = 0; r0 < kArrays * kBlk; r0 += kRowsPerInst) {
+                        const int row = r0 + rsub;                       // (array, SNP slot) = (row / 8, row % 8)
+                        const int a = row / kBlk, t = row % kBlk;
+                        const int idt = __shfl_sync(0xffffffffu, idr, t);
+                        if (row < kArrays * kBlk) {
+                            const double* base = a == 0 ? P.gam : a == 1 ? P.mu : a == 2 ? P.dtab : a == 3 ? P.wtab : P.i0tab;
+                            cp_async16(stg + (size_t)row * kT + csub, base + (size_t)(idt < 0 ? 0 : idt) * P.q_pad + kcol);
                         }
                     }
                     cp_async_commit();
@@ -462,6 +463,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     AQ_T0();
                     double* io = iobuf + (size_t)(g & 1) * kBlk * 2 * kT;
                     cp_async_wait_all();  // issued a whole block earlier
+                    __syncwarp();         // (each lane waited for its own copies; the rows are read by other lanes)
 #pragma unroll
                     for (int i = 0; i < kTP; ++i) {
                         const int t = t0 + i;
