@@ -639,7 +639,7 @@ int launch_mis(aq_ctx* c, int mode, double cc, double log_sig2_inv, double sig2_
     P.sig2_inv = sig2_inv;
     P.out = c->mis_out;
     P.mode = mode;
-    const int warps = 8, grid = (c->q + warps - 1) / warps;
+    const int warps = 4, grid = (c->q + warps - 1) / warps;
     const int M = (c->n + 31) / 32;
     AQ_CUDA(cudaEventRecord(c->ev0, c->stream));
     if (M <= 4) mis_sweep_kernel<4><<<grid, warps * 32, 0, c->stream>>>(P);

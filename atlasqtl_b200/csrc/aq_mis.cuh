@@ -49,8 +49,13 @@ enum {
     kMisOutputs
 };
 
+// n <= 512: X columns are consumed in chunks of 8 values per lane (and re-read from L1 for the rank-1 update) so that the
+// kernel fits in 128 registers: 16 warps per SM instead of 8 hide the per-SNP latency (reduction, logistic).  Beyond, a
+// column is loaded once per SNP and kept in registers (8 warps per SM): the path is then bound by L1 bandwidth, one
+// 8n-byte column read per update (the register-blocked remedy needs per-trait Gram corrections: next round).
 template <int M>
-__global__ void __launch_bounds__(256) mis_sweep_kernel(const MisParams P) {
+__global__ void __launch_bounds__(128, (M <= 16) ? 4 : 2) mis_sweep_kernel(const MisParams P) {
+    constexpr int kXC = M <= 16 ? (M < 8 ? M : 8) : M;
     const int lane = threadIdx.x & 31;
     const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // one warp per trait
     if (k >= P.q) return;
@@ -93,18 +98,16 @@ __global__ void __launch_bounds__(256) mis_sweep_kernel(const MisParams P) {
             const int j = __shfl_sync(0xffffffffu, jl, t);
             if (j < 0) continue;   // warp-uniform
             const double* x = P.xraw + (size_t)j * P.n;
-            double xv[M];
-#pragma unroll
-            for (int m = 0; m < M; ++m) {
-                const int i = lane + 32 * m;
-                xv[m] = i < P.n ? __ldg(x + i) : 0.0;
-            }
             if (P.mode == 2) {   // X_norm_sq(j,k) = sum_i x_ij^2 mis_ik
                 double q0 = 0.0, q1 = 0.0;
 #pragma unroll
-                for (int m = 0; m < M; m += 2) {
-                    if ((mbits >> m) & 1ull) q0 = fma(xv[m], xv[m], q0);
-                    if (m + 1 < M && ((mbits >> (m + 1)) & 1ull)) q1 = fma(xv[m + 1], xv[m + 1], q1);
+                for (int m = 0; m < M; ++m) {
+                    const int i = lane + 32 * m;
+                    const double xv = i < P.n ? __ldg(x + i) : 0.0;
+                    if ((mbits >> m) & 1ull) {
+                        if (m & 1) q1 = fma(xv, xv, q1);
+                        else q0 = fma(xv, xv, q0);
+                    }
                 }
                 const double qs = warp_sum(q0 + q1);
                 if (lane == t) xnew = qs;
@@ -114,11 +117,20 @@ __global__ void __launch_bounds__(256) mis_sweep_kernel(const MisParams P) {
             if (P.mode == 0) {
                 double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
 #pragma unroll
-                for (int m = 0; m < M; m += 4) {
-                    d0 = fma(xv[m], r[m], d0);
-                    if (m + 1 < M) d1 = fma(xv[m + 1], r[m + 1], d1);
-                    if (m + 2 < M) d2 = fma(xv[m + 2], r[m + 2], d2);
-                    if (m + 3 < M) d3 = fma(xv[m + 3], r[m + 3], d3);
+                for (int m0 = 0; m0 < M; m0 += kXC) {
+                    double xv[kXC];
+#pragma unroll
+                    for (int e = 0; e < kXC; ++e) {
+                        const int i = lane + 32 * (m0 + e);
+                        xv[e] = i < P.n ? __ldg(x + i) : 0.0;
+                    }
+#pragma unroll
+                    for (int e = 0; e < kXC; e += 4) {
+                        d0 = fma(xv[e], r[m0 + e], d0);
+                        if (e + 1 < kXC) d1 = fma(xv[e + 1], r[m0 + e + 1], d1);
+                        if (e + 2 < kXC) d2 = fma(xv[e + 2], r[m0 + e + 2], d2);
+                        if (e + 3 < kXC) d3 = fma(xv[e + 3], r[m0 + e + 3], d3);
+                    }
                 }
                 const double dot = warp_sum((d0 + d1) + (d2 + d3));
                 const double bo_t = __shfl_sync(0xffffffffu, bo, t), xn_t = __shfl_sync(0xffffffffu, xn, t);
@@ -133,8 +145,17 @@ __global__ void __launch_bounds__(256) mis_sweep_kernel(const MisParams P) {
                 dlt = __shfl_sync(0xffffffffu, bo, t);                 // r = mis o (y - X beta): subtract beta_jk x_j
             }
 #pragma unroll
-            for (int m = 0; m < M; ++m)
-                if ((mbits >> m) & 1ull) r[m] = fma(-dlt, xv[m], r[m]);   // :132
+            for (int m0 = 0; m0 < M; m0 += kXC) {   // (the column is still in L1)
+                double xv[kXC];
+#pragma unroll
+                for (int e = 0; e < kXC; ++e) {
+                    const int i = lane + 32 * (m0 + e);
+                    xv[e] = i < P.n ? __ldg(x + i) : 0.0;
+                }
+#pragma unroll
+                for (int e = 0; e < kXC; ++e)
+                    if ((mbits >> (m0 + e)) & 1ull) r[m0 + e] = fma(-dlt, xv[e], r[m0 + e]);   // :132
+            }
         }
         // ---- one SNP per lane again: results and running sums
         if (jl >= 0) {
