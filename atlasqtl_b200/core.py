@@ -138,11 +138,67 @@ def _e_sig2_inv(nu, nu_vb, log_sig2_inv_vb, rho, rho_vb, sig2_inv_vb):
             - nu_vb * math.log(rho_vb) - sp.gammaln(nu) + sp.gammaln(nu_vb))  # R/elbo.R:41-46
 
 
+# ----------------------------------------------------------------------------- checkpoints (R/utils.R:571-627)
+def _checkpoint_file(checkpoint_path, it, rank, world_size):
+    tag = "" if world_size == 1 else f"_slab{rank}"
+    return f"{checkpoint_path}tmp_output_it_{it}{tag}.npz"
+
+
+def checkpoint_(it, checkpoint_path, ctx, theta_vb, zeta_vb, converged, lb_new, lb_old, lam2_inv_vb=None,
+                sig02_inv_vb=None, rate=100, comm=None, extra=None):
+    """Every `rate` iterations: the device -> host hand-off of gam_vb / beta_vb (aq_get_state) and the fields the
+    reference saves (`tmp_vb`, R/utils.R:596-602), keeping the last two files (:604-607).  One file per trait slab.
+    `extra` adds what a RESUME needs (mu_beta_vb, tau_vb, ...), which the reference's checkpoints lack."""
+    if checkpoint_path is None or it % rate != 0:
+        return None
+    rank, world = (comm.rank, comm.world_size) if comm is not None else (0, 1)
+    st = ctx.get_state(gam=True, mu=extra is not None, beta=True)
+    fields = dict(beta_vb=st["beta_vb"], gam_vb=st["gam_vb"], theta_vb=theta_vb, zeta_vb=zeta_vb,
+                  converged=converged, it=it, lb_new=lb_new, diff_lb=abs(lb_new - lb_old))
+    if lam2_inv_vb is not None:
+        fields["lam2_inv_vb"] = lam2_inv_vb
+    if sig02_inv_vb is not None:
+        fields["sig02_inv_vb"] = sig02_inv_vb
+    if extra is not None:
+        fields["mu_beta_vb"] = st["mu_beta_vb"]
+        fields.update(extra)
+    path = _checkpoint_file(checkpoint_path, it, rank, world)
+    np.savez(path, **fields)
+    old = _checkpoint_file(checkpoint_path, it - 2 * rate, rank, world)
+    if os.path.exists(old):
+        os.remove(old)
+    return path
+
+
+def checkpoint_clean_up_(checkpoint_path, comm=None):
+    """R/utils.R:612-625: remove the temporary files once the run has finished."""
+    if checkpoint_path is None:
+        return
+    import glob
+    rank, world = (comm.rank, comm.world_size) if comm is not None else (0, 1)
+    tag = "" if world == 1 else f"_slab{rank}"
+    for f in glob.glob(f"{checkpoint_path}tmp_output_it_*{tag}.npz"):
+        os.remove(f)
+
+
+def init_from_checkpoint(path, list_init):
+    """Extension (the reference cannot resume): a list_init that restarts the run from a checkpoint written with the
+    resume fields.  theta_vb, zeta_vb, gam_vb, mu_beta_vb, tau_vb, sig2_beta_vb, sig2_theta_vb, sig02_inv_vb are taken
+    from the file, everything else from `list_init`."""
+    d = np.load(path)
+    out = dict(list_init)
+    for key in ("gam_vb", "mu_beta_vb", "theta_vb", "zeta_vb", "tau_vb", "sig2_beta_vb", "sig2_theta_vb"):
+        out[key] = np.array(d[key])
+    out["sig02_inv_vb"] = float(d["sig02_inv_vb"])
+    return out
+
+
 # ----------------------------------------------------------------------------- the core
 def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbose, list_hyper, list_init,
                                 checkpoint_path=None, trace_path=None, full_output=False,
                                 thinned_elbo_eval=True, debug=False, batch="y", *, comm=None, slab=None,
-                                device=0, context_factory=None, order_fn=None, trace=None, ctx=None, iter_hook=None):
+                                device=0, context_factory=None, order_fn=None, trace=None, ctx=None, iter_hook=None,
+                                checkpoint_rate=100, keep_checkpoints=False):
     """Same positional arguments as the reference core (R/atlasqtl_global_local_core.R:8-13).
 
     Y is THIS process's slab of responses (all of Y when comm is None); `slab` = (k_first, k_last)
@@ -157,8 +213,8 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
     if np.isnan(Y).any():  # :19-33 (X_norm_sq and the per-trait Gram corrections live on the device)
         mis_pat = np.where(np.isnan(Y), 0.0, 1.0)
         Y = np.where(np.isnan(Y), 0.0, Y)
-    if checkpoint_path is not None or trace_path is not None:
-        raise NotImplementedError("checkpoint_path / trace_path are host-side I/O outside this path")
+    if trace_path is not None:
+        raise NotImplementedError("trace_path (diagnostic plots of the hotspot variances) is outside this path")
     comm = comm or SerialComm()
     n, q = Y.shape
     p = X.shape[1]
@@ -387,7 +443,12 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
                 rec["c_next"] = c
                 rec["c"] = c_prev
                 trace.append(rec)
+            checkpoint_(it, checkpoint_path, ctx, theta_vb, zeta_vb, converged, lb_new, lb_old, lam2_inv_vb, sig02_inv_vb,
+                        comm=comm, rate=checkpoint_rate,
+                        extra=dict(tau_vb=tau_vb, sig2_beta_vb=sig2_beta_vb, sig2_theta_vb=sig2_theta_vb))  # :379-381
 
+        if not keep_checkpoints:
+            checkpoint_clean_up_(checkpoint_path, comm)  # :388
         if iter_hook is not None:
             iter_hook(it + 1, ctx)
         if verbose != 0 and comm.rank == 0:

@@ -49,7 +49,36 @@ def test_rejects_what_this_build_does_not_cover():
     with pytest.raises(ValueError):
         core.atlasqtl_global_local_core_(Y, X, 5, None, 1, 0.1, 5, 0, hyper, init, batch="0")
     with pytest.raises(NotImplementedError):
-        core.atlasqtl_global_local_core_(Y, X, 5, None, 1, 0.1, 5, 0, hyper, init, checkpoint_path="/tmp/x")
+        core.atlasqtl_global_local_core_(Y, X, 5, None, 1, 0.1, 5, 0, hyper, init, trace_path="/tmp/x")
+
+
+def test_checkpoints_and_resume(oracle_built, tmp_path):
+    """checkpoint_ / checkpoint_clean_up_ (R/utils.R:571-627): files every `rate` iterations with the reference's fields,
+    only the last two kept, removed at the end; and (extension) a run restarted from a checkpoint lands on the same
+    optimum."""
+    import glob
+    X, Y, hyper, init = make_problem(100, 75, 20, p_act=10, q_act=20, maf=0.2, p0=(5, 25))
+    q = Y.shape[1]
+    base = str(tmp_path) + "/"
+    fac = lambda X_, Y_: OracleSweepContext(X_, Y_)
+    ref = core.atlasqtl_global_local_core_(Y, X, q, None, 1, 0.1, 1000, 0, hyper, init, context_factory=fac)
+    out = core.atlasqtl_global_local_core_(Y, X, q, None, 1, 0.1, 1000, 0, hyper, init, checkpoint_path=base,
+                                           checkpoint_rate=10, keep_checkpoints=True, context_factory=fac)
+    assert np.array_equal(out["gam_vb"], ref["gam_vb"])            # checkpointing does not perturb the run
+    files = sorted(glob.glob(base + "tmp_output_it_*.npz"), key=lambda f: int(f.split("_it_")[1][:-4]))
+    its = [int(f.split("_it_")[1][:-4]) for f in files]
+    assert its == [i for i in range(10, out["it"] + 1, 10)][-2:]   # only the last two are kept
+    d = np.load(files[0])
+    for key in ("beta_vb", "gam_vb", "theta_vb", "zeta_vb", "converged", "it", "lb_new", "diff_lb", "lam2_inv_vb",
+                "sig02_inv_vb"):
+        assert key in d.files
+    assert d["gam_vb"].shape == (X.shape[1], q) and int(d["it"]) == its[0]
+    init2 = core.init_from_checkpoint(files[0], init)
+    res = core.atlasqtl_global_local_core_(Y, X, q, None, 1, 0.1, 1000, 0, hyper, init2, checkpoint_path=base,
+                                           checkpoint_rate=10, context_factory=fac)
+    assert res["converged"]
+    assert np.abs(res["gam_vb"] - ref["gam_vb"]).max() <= 1e-2 and abs(res["lb_opt"] - ref["lb_opt"]) <= 1.0  # tol = 0.1 on the ELBO
+    assert glob.glob(base + "tmp_output_it_*.npz") == []           # cleaned up at the end by default
 
 
 @pytest.mark.parametrize("anneal", [None, (1, 2, 5)])
