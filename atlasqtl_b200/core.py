@@ -39,6 +39,15 @@ class SerialComm:
 
 # ----------------------------------------------------------------------------- small host helpers
 _POOL = None
+_BG = None
+
+
+def _background():
+    """One host thread for work that overlaps the (GIL-releasing) sweep call."""
+    global _BG
+    if _BG is None:
+        _BG = ThreadPoolExecutor(1)
+    return _BG
 
 
 def _pmap(fn, x, min_chunk=4096):
@@ -326,6 +335,18 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
             if order_fn is not None and it > 1:
                 ctx.set_order(np.ascontiguousarray(order_fn(it, p), dtype=np.int32))  # :160-163
 
+            # The horseshoe scale update (:241-254) reads only the PREVIOUS theta_vb / sig2_theta_vb / sig02_inv_vb, so its
+            # p-vector special functions (incomplete gammas, E1 / Lentz) run on a host thread while the GPU sweeps; the
+            # statements and their operands are unchanged, only the wall-clock position moves.
+            def _hs_scale(c_s=c_s, theta=theta_vb, s2t=sig2_theta_vb, s02=sig02_inv_vb, ann=annealing and anneal_scale):
+                th2_ = theta ** 2 + s2t - 2 * theta * m0 + m0 ** 2
+                L_ = c_s * s02 * shr_fac_inv * th2_ / 2 / df  # :241
+                if ann:
+                    return L_, None, update_annealed_lam2_inv_vb_(L_, c_s, df)  # :246
+                Q_ = Q_approx_vec(L_)  # :250
+                return L_, Q_, 1 / (Q_ * L_) - 1  # :254
+            hs_future = _background().submit(_hs_scale)
+
             # ---- the sweep (:167-170) with the fused reductions
             if mis_pat is None:
                 sums = ctx.sweep(c, log_sig2_inv_vb, tau_vb, log_tau_vb, sig2_beta_vb)
@@ -343,14 +364,10 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
             rowsums_Z = rowsum_zpart / sqrt_c + q_total * theta_vb + sum_zeta  # :237
             colsums_Z = sums["colsum_zpart"] / sqrt_c + theta_vb.sum() + p * zeta_vb
 
-            th2 = theta_vb ** 2 + sig2_theta_vb - 2 * theta_vb * m0 + m0 ** 2
-            L_vb = c_s * sig02_inv_vb * shr_fac_inv * th2 / 2 / df  # :241
             rho_xi_inv_vb = c_s * (A2_inv + sig02_inv_vb)  # :242
-            if annealing and anneal_scale:
-                lam2_inv_vb = update_annealed_lam2_inv_vb_(L_vb, c_s, df)  # :246
-            else:
-                Q_app = Q_approx_vec(L_vb)  # :250
-                lam2_inv_vb = 1 / (Q_app * L_vb) - 1  # :254
+            L_vb, Q_new, lam2_inv_vb = hs_future.result()
+            if Q_new is not None:
+                Q_app = Q_new
             xi_inv_vb = nu_xi_inv_vb / rho_xi_inv_vb  # :276
             prior_prec = sig02_inv_vb * lam2_inv_vb * shr_fac_inv
             sig2_theta_vb = 1 / (c * (q_total + prior_prec))  # :278
