@@ -49,18 +49,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// non-blocking probe (try_wait may suspend the warp for a while when the phase is still pending)
-__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
@@ -72,10 +60,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  : "memory");
 }
 
-// 8-byte asynchronous copy global -> shared (SASS: LDGSTS), tracked per thread by commit / wait groups
-__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src_gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
-}
+// 16-byte asynchronous copy global -> shared (SASS: LDGSTS), tracked per thread by commit / wait groups
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
@@ -104,9 +89,6 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* local_smem, uint32_t ra
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local_smem)), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void st_cluster_v2(uint32_t raddr, double a, double b) {
-    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(raddr), "d"(a), "d"(b) : "memory");
-}
 __device__ __forceinline__ void st_cluster_f64(uint32_t raddr, double a) {
     asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(raddr), "d"(a) : "memory");
 }
@@ -117,7 +99,6 @@ __device__ __forceinline__ void st_async_v2(uint32_t raddr, double a, double b, 
                  "d"(b), "r"(rbar)
                  : "memory");
 }
-__device__ __forceinline__ void fence_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t raddr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
@@ -193,7 +174,6 @@ __device__ __forceinline__ double logistic_neg(double x) {
     // beyond +-700 the function is 0 / 1 to 1e-304 and the pieces above are meaningless; NaN falls through
     return x > 700.0 ? 0.0 : (x < -700.0 ? 1.0 : y);
 }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---------------------------------------------------------------- normal-distribution helpers
 // log Phi(x), accurate in both tails: Phi(x) = erfc(-x/sqrt2)/2; for x < -1 go through the scaled

@@ -17,8 +17,9 @@
 //                   band (S[u] -= G[t][u] Delta[t]), evaluates mu / gam (annealed logistic) / beta and emits
 //                   -Delta.  It is the only serial dependency of the sweep (block b+1 needs Delta_b), so it
 //                   touches shared memory only; everything else of a block is done around it by the
-//   1 "helper" warp which sums the split-K partials of S, fetches the block's beta_old and c (D + cst) from the
-//                   p x q arrays one block ahead, writes gam / mu back and keeps the per-trait running sums.
+//   1 "helper" warp which sums the split-K partials of S, stages the block's beta_old and c (D + cst) in shared memory
+//                   (p x q rows fetched by cp.async one block ahead), writes gam / mu back and keeps the per-trait
+//                   running sums.
 //
 // One-block look-ahead hides the serial chain behind the tensor pipe: S'_{b+1} = X_{b+1}' R_{b-1} is formed
 // while the chain of block b runs, and corrected by the cross Gram block, S_{b+1} = S'_{b+1} - G_{b+1,b} Delta_b;
