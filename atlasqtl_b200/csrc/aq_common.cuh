@@ -175,18 +175,4 @@ __device__ __forceinline__ double logistic_neg(double x) {
     return x > 700.0 ? 0.0 : (x < -700.0 ? 1.0 : y);
 }
 
-// ---------------------------------------------------------------- normal-distribution helpers
-// log Phi(x), accurate in both tails: Phi(x) = erfc(-x/sqrt2)/2; for x < -1 go through the scaled
-// complementary error function so that nothing underflows; for x > 0 use log1p(-Q(x)).
-// (Replaces R's pnorm(x, log.p = TRUE), R/atlasqtl_global_local_core.R:62-63,294-295.)
-__device__ __forceinline__ double log_ndtr(double x) {
-    const double rs2 = 0.70710678118654752440;
-    if (x < -1.0) {
-        double t = -x * rs2;
-        return log(0.5 * erfcx(t)) - t * t;
-    }
-    if (x > 0.0) return log1p(-0.5 * erfc(x * rs2));
-    return log(0.5 * erfc(-x * rs2));
-}
-
 }  // namespace aq
