@@ -86,7 +86,10 @@ struct SweepCfg {
     static constexpr size_t kTileDoubles = (size_t)kBlk * kXS + kTileTail;
     static constexpr int kSps = 10;  // S-partial row stride (doubles): 8 SNP slots + 2 pad => conflict-free 16-byte accesses
     static constexpr size_t kSpartDoubles = (size_t)WS * kT * kSps;      // [WS][kT][kSps], single-buffered (sfree barrier)
-    static constexpr size_t kSsumDoubles = (size_t)2 * kT * kSps;        // [2][kT][kSps] summed S tile for the chain
+    // who sums the split-K partials of S: the chain warp itself (single CTA: one hop less between the tensor work and the
+    // recurrence), or the helper warp (clusters: the wait for the other CTAs' slices stays off the serial path)
+    static constexpr bool kChainSums = !kCl;
+    static constexpr size_t kSsumDoubles = kChainSums ? 0 : (size_t)2 * kT * kSps;  // [2][kT][kSps] summed S tile for the chain
     static constexpr size_t kDbufDoubles = (size_t)2 * kT * kBlk;
     static constexpr size_t kRsqDoubles = (size_t)WS * kT;
     static constexpr size_t kIoDoubles = (size_t)2 * kBlk * 2 * kT;  // [2][kBlk][2][kT]: in beta_old, c (D + cst); out gam, mu
@@ -107,6 +110,54 @@ struct SweepCfg {
     static_assert(kSmemBytes <= 232448, "shared memory budget (227 KB)");
 };
 
+// S = X_b' R of one block: sums this CTA's WS split-K partials and, on a cluster leader, the tiles the other CTAs shipped.
+// Lane layout: trait `tsum`, and with <= 16 traits per tile the two half-warps split the partials of a trait between them.
+// On return every lane holds the complete S row of its trait.  Called by the chain warp (single CTA) or the helper warp.
+template <class Cfg>
+__device__ __forceinline__ void sum_s_partials(double (&s)[kBlk], const double* spart, const double* red, uint64_t* sfree,
+                                               uint64_t* sred, long gb, int ncta, int lane, int tsum) {
+    constexpr int WS = Cfg::WS, kT = Cfg::kT;
+    constexpr int kH = (kT <= 16) ? 2 : 1;
+    constexpr int kW0 = (WS + kH - 1) / kH;
+    const int half = (kH == 2) ? (lane >> 4) : 0;
+    const double* sp0 = spart + tsum * Cfg::kSps;
+#pragma unroll
+    for (int t = 0; t < kBlk; ++t) s[t] = 0.0;
+#pragma unroll
+    for (int w2 = 0; w2 < kW0; ++w2) {
+        const int w = half * kW0 + w2;
+        if (kH == 1 || w < WS) {
+#pragma unroll
+            for (int t = 0; t < kBlk; t += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(sp0 + w * kT * Cfg::kSps + t);
+                s[t] += v.x;
+                s[t + 1] += v.y;
+            }
+        }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sfree[0]);  // the MMA warps may overwrite the partials
+    if (Cfg::kCl && ncta > 1) {  // + the other sample slices, already reduced (and stored here) by their CTAs
+        if (lane == 0) mbar_arrive_expect_tx(&sred[gb & 1], (uint32_t)(ncta - 1) * Cfg::kDeltaBytes);
+        mbar_wait(&sred[gb & 1], (uint32_t)((gb >> 1) & 1));
+        if (half == 0) {
+            for (int r2 = 1; r2 < ncta; ++r2) {
+                const double* rp = red + ((size_t)((gb & 1) * (kMaxCluster - 1) + (r2 - 1)) * kT + tsum) * Cfg::kSps;
+#pragma unroll
+                for (int t = 0; t < kBlk; t += 2) {
+                    const double2 v = *reinterpret_cast<const double2*>(rp + t);
+                    s[t] += v.x;
+                    s[t + 1] += v.y;
+                }
+            }
+        }
+    }
+    if (kH == 2) {
+#pragma unroll
+        for (int t = 0; t < kBlk; ++t) s[t] += __shfl_xor_sync(0xffffffffu, s[t], 16);
+    }
+}
+
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepParams P) {
     constexpr int WS = Cfg::WS, MT = Cfg::MT, NT = Cfg::NT, kT = Cfg::kT, XS = Cfg::kXS;
@@ -115,7 +166,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* tiles = reinterpret_cast<double*>(smem_raw);
     double* spart = tiles + kStages * Cfg::kTileDoubles;  // [WS][kT][kSps]
-    double* ssum = spart + Cfg::kSpartDoubles;            // [2][kT][kSps]
+    double* ssum = spart + Cfg::kSpartDoubles;            // [2][kT][kSps]  (clustered variant only)
     double* dbuf = ssum + Cfg::kSsumDoubles;              // [2][kT][kBlk]  (holds -Delta)
     double* rsqs = dbuf + Cfg::kDbufDoubles;              // [WS][kT]
     double* iobuf = rsqs + Cfg::kRsqDoubles;              // [2][kBlk][2][kT]
@@ -420,7 +471,6 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
         if (P.mode == 0 && rank == 0) {
             constexpr int kH = (kT <= 16) ? 2 : 1;
             constexpr int kTP = kBlk / kH;           // SNP slots per lane
-            constexpr int kW0 = (WS + kH - 1) / kH;  // split-K partials per lane
             // W / I0 of a block: staged with the other rows when a lane handles 4 SNP slots; with 8 slots per lane (T > 16)
             // the extra asynchronous copies cost more than they hide, and W / I0 are requested directly one block ahead
             constexpr bool kStageWI = (kH == 2);
@@ -481,54 +531,19 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                         }
                     }
                     if (blk + 1 < nb) stage_rows(blk + 1);
-                    mbar_wait(&sdone[g & 1], (uint32_t)((g >> 1) & 1));
-                    AQ_T(4);
-                    const double* sp0 = spart + tls * Cfg::kSps;
-                    double s[kBlk];
-#pragma unroll
-                    for (int t = 0; t < kBlk; ++t) s[t] = 0.0;
-#pragma unroll
-                    for (int w2 = 0; w2 < kW0; ++w2) {
-                        const int w = half * kW0 + w2;
-                        if (kH == 1 || w < WS) {
+                    if (!Cfg::kChainSums) {
+                        mbar_wait(&sdone[g & 1], (uint32_t)((g >> 1) & 1));
+                        AQ_T(4);
+                        double s[kBlk];
+                        sum_s_partials<Cfg>(s, spart, red, sfree, sred, g, ncta, lane, tls);
+                        if (half == 0 && active) {
 #pragma unroll
                             for (int t = 0; t < kBlk; t += 2) {
-                                const double2 v = *reinterpret_cast<const double2*>(sp0 + w * kT * Cfg::kSps + t);
-                                s[t] += v.x;
-                                s[t + 1] += v.y;
+                                double2 v;
+                                v.x = s[t];
+                                v.y = s[t + 1];
+                                *reinterpret_cast<double2*>(ssum + ((size_t)(g & 1) * kT + tl) * Cfg::kSps + t) = v;
                             }
-                        }
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&sfree[0]);  // the MMA warps may overwrite the partials
-                    if (kCl && ncta > 1) {  // + the other sample slices, already reduced (and stored here) by their CTAs
-                        if (lane == 0) mbar_arrive_expect_tx(&sred[g & 1], (uint32_t)(ncta - 1) * Cfg::kDeltaBytes);
-                        AQ_T(5);
-                        mbar_wait(&sred[g & 1], (uint32_t)((g >> 1) & 1));
-                        AQ_T(6);
-                        if (half == 0) {
-                            for (int r2 = 1; r2 < ncta; ++r2) {
-                                const double* rp = red + ((size_t)((g & 1) * (kMaxCluster - 1) + (r2 - 1)) * kT + tls) * Cfg::kSps;
-#pragma unroll
-                                for (int t = 0; t < kBlk; t += 2) {
-                                    const double2 v = *reinterpret_cast<const double2*>(rp + t);
-                                    s[t] += v.x;
-                                    s[t + 1] += v.y;
-                                }
-                            }
-                        }
-                    }
-                    if (kH == 2) {
-#pragma unroll
-                        for (int t = 0; t < kBlk; ++t) s[t] += __shfl_xor_sync(0xffffffffu, s[t], 16);
-                    }
-                    if (half == 0 && active) {
-#pragma unroll
-                        for (int t = 0; t < kBlk; t += 2) {
-                            double2 v;
-                            v.x = s[t];
-                            v.y = s[t + 1];
-                            *reinterpret_cast<double2*>(ssum + ((size_t)(g & 1) * kT + tl) * Cfg::kSps + t) = v;
                         }
                     }
                     __syncwarp();
@@ -598,6 +613,10 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
         const int tl = lane;
         const bool active = tl < kT;
         const int tls = active ? tl : 0;  // inactive lanes shadow trait 0 without side effects
+        // summation of the S partials: lanes 16-31 take the second half of the partials of trait (lane & 15) when kT <= 16;
+        // they then shadow that trait through the recurrence, still without side effects
+        const int tsum0 = (kT <= 16) ? (lane & 15) : lane;
+        const int tsum = tsum0 < kT ? tsum0 : 0;
         // -Delta leaves for this CTA's MMA warps (which forward it to the other CTAs of a cluster): this warp never issues
         // a remote operation, they would sit in its load/store queue on the serial path
         auto publish = [&](long gb, const double (&nd)[kBlk]) {
@@ -632,21 +651,29 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     const int stage = (int)(gb % kStages);
                     mbar_wait(&full[stage], (uint32_t)((gb / kStages) & 1));
                     const double* gband = tiles + stage * Cfg::kTileDoubles + kBlk * XS;
-                    mbar_wait(&inready[gb & 1], (uint32_t)((gb >> 1) & 1));
-                    AQ_T(0);
-                    const double* sp0 = ssum + ((size_t)(gb & 1) * kT + tls) * Cfg::kSps;
+                    mbar_wait(&inready[gb & 1], (uint32_t)((gb >> 1) & 1));   // beta_old, c (D + cst): staged a block ahead
                     double* io = iobuf + (size_t)(gb & 1) * kBlk * 2 * kT;
                     double s[kBlk], bo[kBlk], ap[kBlk], nd[kBlk];
 #pragma unroll
-                    for (int t = 0; t < kBlk; t += 2) {
-                        const double2 v = *reinterpret_cast<const double2*>(sp0 + t);
-                        s[t] = v.x;
-                        s[t + 1] = v.y;
-                    }
-#pragma unroll
                     for (int t = 0; t < kBlk; ++t) {
-                        bo[t] = io[(t * 2 + 0) * kT + tls];
-                        ap[t] = io[(t * 2 + 1) * kT + tls];
+                        bo[t] = io[(t * 2 + 0) * kT + tsum];
+                        ap[t] = io[(t * 2 + 1) * kT + tsum];
+                    }
+                    if (Cfg::kChainSums) {
+                        // S = X_b' R: this warp sums the split-K partials itself the moment the MMA warps have delivered
+                        // them; no other warp sits between the tensor work and the recurrence
+                        mbar_wait(&sdone[gb & 1], (uint32_t)((gb >> 1) & 1));
+                        AQ_T(0);
+                        sum_s_partials<Cfg>(s, spart, red, sfree, sred, gb, ncta, lane, tsum);
+                    } else {
+                        AQ_T(0);
+                        const double* sp0 = ssum + ((size_t)(gb & 1) * kT + tsum) * Cfg::kSps;
+#pragma unroll
+                        for (int t = 0; t < kBlk; t += 2) {
+                            const double2 v = *reinterpret_cast<const double2*>(sp0 + t);
+                            s[t] = v.x;
+                            s[t + 1] = v.y;
+                        }
                     }
 #pragma unroll
                     for (int t = 0; t < kBlk; ++t) {
