@@ -12,12 +12,17 @@ from . import core, hyper_init, prepare
 def atlasqtl(Y, X, p0, anneal=(1, 2, 10), tol=0.1, maxit=1000, user_seed=None, verbose=1, list_hyper=None,
              list_init=None, save_hyper=False, save_init=False, full_output=False, thinned_elbo_eval=True,
              checkpoint_path=None, trace_path=None, add_collinear_back=False, *, device=0, comm=None, order_fn=None,
-             trace=None, context_factory=None):
+             trace=None, context_factory=None, prepare_on_device=False, packed_n=None):
+    """prepare_on_device=True runs prepare_data_'s X / Y work on the GPU (X standardised there, never materialised on
+    the host); with packed_n = n, X holds packed 2-bit genotype calls (`device.pack_genotypes`) instead of doubles."""
     if verbose not in (0, 1, 2):
         raise ValueError("The verbose argument must be set to 0, 1 or 2.")
     core.check_annealing_(anneal)
-    dat = prepare.prepare_data_(Y, X, tol, maxit, user_seed, verbose)
-    Xp, Yp = dat["X"], dat["Y"]
+    if prepare_on_device or packed_n is not None:
+        dat = prepare.prepare_data_device_(Y, X, tol, maxit, user_seed, verbose, packed_n=packed_n, device=device)
+    else:
+        dat = prepare.prepare_data_(Y, X, tol, maxit, user_seed, verbose)
+    Xp, Yp = dat["X"], dat["Y"]  # device path: Xp is a handle with .shape, Yp the raw responses (hyper / init use variances only)
     n, p = Xp.shape
     q = Yp.shape[1]
     shr_fac_inv = q  # R/atlasqtl.R:218

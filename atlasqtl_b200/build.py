@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libatlasqtl_b200.so")
 SOURCES = ["aq_api.cu", "aq_compat.cu"]
-HEADERS = ["aq_common.cuh", "aq_stream.cuh", "aq_sweep.cuh", "aq_mis.cuh", "aq_select.cuh", os.path.join("..", "..", "include", "atlasqtl_b200.h")]
+HEADERS = ["aq_common.cuh", "aq_stream.cuh", "aq_sweep.cuh", "aq_mis.cuh", "aq_select.cuh", "aq_prep.cuh", os.path.join("..", "..", "include", "atlasqtl_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 

@@ -21,7 +21,7 @@ from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 from scipy import special as sp
 
-from .device import SweepContext
+from .device import PreparedPredictors, SweepContext
 
 ALL_EQUAL_TOL = 1.5e-8  # isTRUE(all.equal(c, 1))
 
@@ -219,6 +219,7 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
     if batch != "y":
         raise ValueError("Batch scheme not defined. Exit.")  # only the C++ path is replaced (:179-232)
     mis_pat = None
+    Y_raw = Y  # a PreparedPredictors X centres the raw responses on the device (R/prepare_atlasqtl.R:83)
     if np.isnan(Y).any():  # :19-33 (X_norm_sq and the per-trait Gram corrections live on the device)
         mis_pat = np.where(np.isnan(Y), 0.0, 1.0)
         Y = np.where(np.isnan(Y), 0.0, Y)
@@ -277,8 +278,12 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
 
     own_ctx = ctx is None
     if own_ctx:
-        factory = context_factory or (lambda X_, Y_: SweepContext(X_, Y_, device=device))
-        ctx = factory(X, Y)
+        if isinstance(X, PreparedPredictors):
+            ctx = X.context(Y_raw)
+        else:
+            factory = context_factory or (lambda X_, Y_: SweepContext(X_, Y_, device=device))
+            ctx = factory(X, Y)
+    del Y_raw
     try:
         order = None
         if order_fn is not None:

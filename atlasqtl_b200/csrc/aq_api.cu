@@ -6,12 +6,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <numeric>
 #include <string>
 #include <vector>
 
 #include "../../include/atlasqtl_b200.h"
 #include "aq_internal.h"
 #include "aq_mis.cuh"
+#include "aq_prep.cuh"
 #include "aq_select.cuh"
 #include "aq_stream.cuh"
 #include "aq_sweep.cuh"
@@ -113,6 +115,23 @@ struct aq_ctx {
     bool have_state = false, have_tables = false;
     int64_t launches = 0;
     float last_ms = 0.f;
+};
+
+// Pre-processed predictors (aq_prep_x / aq_prep_geno): the raw input stays on the device until a context has
+// materialised the kept, standardised columns from it.
+struct aq_prep {
+    int device = 0, n = 0, p_raw = 0, p_kept = 0;
+    bool geno = false;
+    int bytes_per_col = 0;
+    double* xd = nullptr;
+    uint8_t* gd = nullptr;
+    ColStats* st = nullptr;
+    int* kept_dev = nullptr;
+    cudaStream_t stream = nullptr;
+    std::vector<ColStats> hst;
+    std::vector<uint8_t> status;    // 0 kept, 1 constant, 2 duplicate of dup_of[j]
+    std::vector<int32_t> dup_of, kept;
+    int64_t launches = 0;
 };
 
 namespace {
@@ -373,8 +392,13 @@ int aq_destroy(aq_ctx* c) {
     return AQ_OK;
 }
 
-int aq_create(aq_ctx** out, int device, int n, int p, int q_local, const double* X, const double* Y) {
-    if (!out || !X || !Y) return fail(AQ_EINVAL, "aq_create: NULL argument");
+}  // extern "C"
+
+namespace {
+// X != NULL: standardised predictors from the host (aq_create).  prep != NULL: the kept columns are standardised on the
+// device from the raw input, Y is centred over its observed entries there and n_obs (may be NULL) receives their counts.
+int create_impl(aq_ctx** out, int device, int n, int p, int q_local, const double* X, const aq_prep* prep, const double* Y,
+                double* n_obs) {
     if (n < 2 || p < 1 || q_local < 1) return fail(AQ_EINVAL, "aq_create: need n >= 2, p >= 1, q >= 1");
     CfgInfo cfg;
     if (!pick_cfg(n, &cfg))
@@ -440,15 +464,45 @@ int aq_create(aq_ctx** out, int device, int n, int p, int q_local, const double*
     if (e == cudaSuccess) e = cudaMemsetAsync(c->i0tab, 0, sizeof(double) * pq, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->ovec, 0, sizeof(double) * 5 * (size_t)c->q_pad, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->rowsum, 0, sizeof(double) * c->p_pad, c->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(c->xraw, X, sizeof(double) * (size_t)n * p, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && X) e = cudaMemcpyAsync(c->xraw, X, sizeof(double) * (size_t)n * p, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && prep) {
+        if (prep->geno)
+            materialise_kernel<<<p, 256, 0, c->stream>>>(SrcGeno{prep->gd, prep->bytes_per_col}, n, prep->st, prep->kept_dev, p, c->xraw);
+        else
+            materialise_kernel<<<p, 256, 0, c->stream>>>(SrcDouble{prep->xd, n}, n, prep->st, prep->kept_dev, p, c->xraw);
+        e = cudaGetLastError();
+        c->launches++;
+    }
     // Y: n x q column-major -> [q_pad][n_pad] rows (same orientation, padded leading dimension)
     if (e == cudaSuccess)
         e = cudaMemcpy2DAsync(c->ymat, sizeof(double) * c->ld_resid, Y, sizeof(double) * n, sizeof(double) * n, q_local,
                               cudaMemcpyHostToDevice, c->stream);
+    std::vector<int> n_mis;
+    if (e == cudaSuccess && prep) {
+        // scale(Y, center = TRUE, scale = FALSE) (R/prepare_atlasqtl.R:83); the counts go through the (still unused) order buffer
+        int* n_mis_dev = c->order_dev;
+        if (q_local > c->p_pad) e = cudaMalloc((void**)&n_mis_dev, sizeof(int) * (size_t)q_local);
+        if (e == cudaSuccess) {
+            center_y_kernel<<<(q_local + 7) / 8, 256, 0, c->stream>>>(c->ymat, n, q_local, c->ld_resid, n_mis_dev);
+            e = cudaGetLastError();
+            c->launches++;
+        }
+        n_mis.resize(q_local);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(n_mis.data(), n_mis_dev, sizeof(int) * (size_t)q_local, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (n_mis_dev != c->order_dev) cudaFree(n_mis_dev);
+    }
     if (e != cudaSuccess) {
         cudaGetLastError();
         aq_destroy(c);
         return fail(AQ_ECUDA, std::string("aq_create: ") + cudaGetErrorString(e));
+    }
+    for (int k = 0; k < (int)n_mis.size(); ++k) {
+        if (n_mis[k] >= n) {
+            aq_destroy(c);
+            return fail(AQ_EINVAL, "aq_create_prepared: a column of Y has no observed value");
+        }
+        if (n_obs) n_obs[k] = (double)(n - n_mis[k]);
     }
     // benign per-trait constants for padding traits
     fill_kernel<<<64, 256, 0, c->stream>>>(c->tvec, 3 * (size_t)c->q_pad, 1.0);
@@ -464,6 +518,221 @@ int aq_create(aq_ctx** out, int device, int n, int p, int q_local, const double*
     *out = c;
     return AQ_OK;
 }
+}  // namespace
+
+extern "C" {
+
+int aq_create(aq_ctx** out, int device, int n, int p, int q_local, const double* X, const double* Y) {
+    if (!out || !X || !Y) return fail(AQ_EINVAL, "aq_create: NULL argument");
+    return create_impl(out, device, n, p, q_local, X, nullptr, Y, nullptr);
+}
+
+int aq_create_prepared(aq_ctx** out, const aq_prep* prep, int q_local, const double* Y_raw, double* n_obs) {
+    if (!out || !prep || !Y_raw) return fail(AQ_EINVAL, "aq_create_prepared: NULL argument");
+    if (prep->p_kept < 1) return fail(AQ_EINVAL, "There must be at least 1 non-constant candidate predictor stored in X.");
+    return create_impl(out, prep->device, prep->n, prep->p_kept, q_local, nullptr, prep, Y_raw, n_obs);
+}
+
+int aq_get_x(aq_ctx* c, double* X) {
+    if (!c || !X) return fail(AQ_EINVAL, "aq_get_x: NULL argument");
+    AQ_CUDA(cudaSetDevice(c->device));
+    AQ_CUDA(cudaMemcpyAsync(X, c->xraw, sizeof(double) * (size_t)c->n * c->p, cudaMemcpyDeviceToHost, c->stream));
+    AQ_CUDA(cudaStreamSynchronize(c->stream));
+    return AQ_OK;
+}
+
+int aq_get_y(aq_ctx* c, double* Y) {
+    if (!c || !Y) return fail(AQ_EINVAL, "aq_get_y: NULL argument");
+    AQ_CUDA(cudaSetDevice(c->device));
+    AQ_CUDA(cudaMemcpy2DAsync(Y, sizeof(double) * c->n, c->ymat, sizeof(double) * c->ld_resid, sizeof(double) * c->n, c->q,
+                              cudaMemcpyDeviceToHost, c->stream));
+    AQ_CUDA(cudaStreamSynchronize(c->stream));
+    return AQ_OK;
+}
+
+// ---------------------------------------------------------------- pre-processing of the predictors
+int aq_prep_destroy(aq_prep* P) {
+    if (!P) return AQ_OK;
+    cudaSetDevice(P->device);
+    if (P->stream) cudaStreamSynchronize(P->stream);
+    if (P->xd) cudaFree(P->xd);
+    if (P->gd) cudaFree(P->gd);
+    if (P->st) cudaFree(P->st);
+    if (P->kept_dev) cudaFree(P->kept_dev);
+    if (P->stream) cudaStreamDestroy(P->stream);
+    delete P;
+    return AQ_OK;
+}
+
+}  // extern "C"
+
+namespace {
+template <class Src>
+int prep_verify(aq_prep* P, Src src, const std::vector<int32_t>& pairs, std::vector<int>& differs) {
+    const int npairs = (int)(pairs.size() / 2);
+    differs.assign(npairs, 0);
+    if (!npairs) return AQ_OK;
+    int *pairs_dev = nullptr, *diff_dev = nullptr;
+    AQ_CUDA(cudaMalloc((void**)&pairs_dev, sizeof(int) * pairs.size()));
+    cudaError_t e = cudaMalloc((void**)&diff_dev, sizeof(int) * (size_t)npairs);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pairs_dev, pairs.data(), sizeof(int) * pairs.size(), cudaMemcpyHostToDevice, P->stream);
+    if (e == cudaSuccess) {
+        verify_dups_kernel<<<(npairs + 7) / 8, 256, 0, P->stream>>>(src, P->n, P->st, pairs_dev, npairs, diff_dev);
+        e = cudaGetLastError();
+        P->launches++;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(differs.data(), diff_dev, sizeof(int) * (size_t)npairs, cudaMemcpyDeviceToHost, P->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(P->stream);
+    cudaFree(pairs_dev);
+    if (diff_dev) cudaFree(diff_dev);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(AQ_ECUDA, std::string("aq_prep: ") + cudaGetErrorString(e));
+    }
+    return AQ_OK;
+}
+
+// moments + fingerprints are on the device: classify the columns (constant / duplicate / kept)
+template <class Src>
+int prep_classify(aq_prep* P, Src src) {
+    const int p = P->p_raw;
+    P->hst.resize(p);
+    AQ_CUDA(cudaMemcpyAsync(P->hst.data(), P->st, sizeof(ColStats) * (size_t)p, cudaMemcpyDeviceToHost, P->stream));
+    AQ_CUDA(cudaStreamSynchronize(P->stream));
+    P->status.assign(p, 0);
+    P->dup_of.assign(p, -1);
+    std::vector<int32_t> cand;
+    cand.reserve(p);
+    for (int j = 0; j < p; ++j) {
+        if (P->hst[j].bad)
+            return fail(AQ_EINVAL, P->geno ? "aq_prep_geno: invalid genotype call (code 3) in column " + std::to_string(j)
+                                           : "aq_prep_x: X must not contain missing / non-finite values (column " + std::to_string(j) + ")");
+        if (!(P->hst[j].sd > 0.0)) P->status[j] = 1;   // scale() made it NaN: rm_constant_ (R/utils.R:278)
+        else cand.push_back(j);
+    }
+    // duplicated(mat, MARGIN = 2) (R/utils.R:305): equal fingerprints are suspects, the first of a group is its representative
+    std::sort(cand.begin(), cand.end(), [&](int a, int b) {
+        const ColStats &x = P->hst[a], &y = P->hst[b];
+        if (x.h1 != y.h1) return x.h1 < y.h1;
+        if (x.h2 != y.h2) return x.h2 < y.h2;
+        return a < b;
+    });
+    std::vector<std::vector<int32_t>> groups;   // each: representative first, then its suspects (ascending)
+    for (size_t i = 0; i < cand.size();) {
+        size_t e = i + 1;
+        while (e < cand.size() && P->hst[cand[e]].h1 == P->hst[cand[i]].h1 && P->hst[cand[e]].h2 == P->hst[cand[i]].h2) ++e;
+        if (e - i > 1) groups.emplace_back(cand.begin() + i, cand.begin() + e);
+        i = e;
+    }
+    while (!groups.empty()) {
+        std::vector<int32_t> pairs;
+        for (const auto& g : groups)
+            for (size_t i = 1; i < g.size(); ++i) {
+                pairs.push_back(g[i]);
+                pairs.push_back(g[0]);
+            }
+        std::vector<int> differs;
+        int rc = prep_verify(P, src, pairs, differs);
+        if (rc != AQ_OK) return rc;
+        // a suspect that differs value by value (fingerprint collision) starts / joins a new group, verified next round
+        std::vector<std::vector<int32_t>> next;
+        size_t m = 0;
+        for (const auto& g : groups) {
+            std::vector<int32_t> rest;
+            for (size_t i = 1; i < g.size(); ++i, ++m) {
+                if (differs[m]) rest.push_back(g[i]);
+                else {
+                    P->status[g[i]] = 2;
+                    P->dup_of[g[i]] = g[0];
+                }
+            }
+            if (rest.size() > 1) next.push_back(std::move(rest));
+        }
+        groups.swap(next);
+    }
+    P->kept.clear();
+    for (int j = 0; j < p; ++j)
+        if (P->status[j] == 0) P->kept.push_back(j);
+    P->p_kept = (int)P->kept.size();
+    if (P->p_kept) {
+        AQ_CUDA(cudaMalloc((void**)&P->kept_dev, sizeof(int) * (size_t)P->p_kept));
+        AQ_CUDA(cudaMemcpyAsync(P->kept_dev, P->kept.data(), sizeof(int) * (size_t)P->p_kept, cudaMemcpyHostToDevice, P->stream));
+        AQ_CUDA(cudaStreamSynchronize(P->stream));
+    }
+    return AQ_OK;
+}
+
+int prep_impl(aq_prep** out, int device, int n, int p_raw, const double* X_raw, const uint8_t* geno, int64_t bytes_per_col,
+              int* p_kept) {
+    if (!out || (!X_raw && !geno)) return fail(AQ_EINVAL, "aq_prep: NULL argument");
+    if (n < 2 || p_raw < 1) return fail(AQ_EINVAL, "aq_prep: need n >= 2, p >= 1");
+    if (geno && (bytes_per_col < (n + 3) / 4 || bytes_per_col > (int64_t)1 << 30))
+        return fail(AQ_EINVAL, "aq_prep_geno: bytes_per_col must be at least ceil(n / 4)");
+    int rc = aq_device_info(device, nullptr, nullptr, nullptr);
+    if (rc != AQ_OK) return rc;
+    aq_prep* P = new aq_prep();
+    P->device = device;
+    P->n = n;
+    P->p_raw = p_raw;
+    P->geno = geno != nullptr;
+    P->bytes_per_col = (int)bytes_per_col;
+    cudaError_t e = cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&P->st, sizeof(ColStats) * (size_t)p_raw);
+    if (e == cudaSuccess) {
+        if (geno) {
+            e = cudaMalloc((void**)&P->gd, (size_t)bytes_per_col * p_raw);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(P->gd, geno, (size_t)bytes_per_col * p_raw, cudaMemcpyHostToDevice, P->stream);
+        } else {
+            e = cudaMalloc((void**)&P->xd, sizeof(double) * (size_t)n * p_raw);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(P->xd, X_raw, sizeof(double) * (size_t)n * p_raw, cudaMemcpyHostToDevice, P->stream);
+        }
+    }
+    if (e == cudaSuccess) {
+        if (geno) col_stats_geno_kernel<<<(p_raw + 7) / 8, 256, 0, P->stream>>>(SrcGeno{P->gd, P->bytes_per_col}, n, p_raw, P->st);
+        else col_stats_double_kernel<<<(p_raw + 7) / 8, 256, 0, P->stream>>>(SrcDouble{P->xd, n}, p_raw, P->st);
+        e = cudaGetLastError();
+        P->launches++;
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        aq_prep_destroy(P);
+        return fail(e == cudaErrorMemoryAllocation ? AQ_ENOMEM : AQ_ECUDA, std::string("aq_prep: ") + cudaGetErrorString(e));
+    }
+    rc = geno ? prep_classify(P, SrcGeno{P->gd, P->bytes_per_col}) : prep_classify(P, SrcDouble{P->xd, n});
+    if (rc != AQ_OK) {
+        aq_prep_destroy(P);
+        return rc;
+    }
+    if (p_kept) *p_kept = P->p_kept;
+    *out = P;
+    return AQ_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int aq_prep_x(aq_prep** out, int device, int n, int p_raw, const double* X_raw, int* p_kept) {
+    if (!X_raw) return fail(AQ_EINVAL, "aq_prep_x: NULL argument");
+    return prep_impl(out, device, n, p_raw, X_raw, nullptr, 0, p_kept);
+}
+
+int aq_prep_geno(aq_prep** out, int device, int n, int p_raw, const uint8_t* geno, int64_t bytes_per_col, int* p_kept) {
+    if (!geno) return fail(AQ_EINVAL, "aq_prep_geno: NULL argument");
+    return prep_impl(out, device, n, p_raw, nullptr, geno, bytes_per_col, p_kept);
+}
+
+int aq_prep_result(const aq_prep* P, uint8_t* status, int32_t* dup_of, double* mean, double* sd) {
+    if (!P) return fail(AQ_EINVAL, "aq_prep_result: NULL argument");
+    for (int j = 0; j < P->p_raw; ++j) {
+        if (status) status[j] = P->status[j];
+        if (dup_of) dup_of[j] = P->dup_of[j];
+        if (mean) mean[j] = P->hst[j].mean;
+        if (sd) sd[j] = P->hst[j].sd;
+    }
+    return AQ_OK;
+}
+
+int64_t aq_prep_launch_count(const aq_prep* P) { return P ? P->launches : 0; }
 
 int aq_dims(const aq_ctx* c, int* n, int* p, int* q_local, int* p_pad, int* q_pad) {
     if (!c) return fail(AQ_EINVAL, "NULL context");

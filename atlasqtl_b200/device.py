@@ -22,6 +22,33 @@ class SweepContext:
                                        _lib.dptr(X), _lib.dptr(Y)))
         self.device = device
 
+    @classmethod
+    def from_prepared(cls, prep, Y_raw):
+        """Context over the kept, device-standardised columns of `prep` (aq_create_prepared): Y_raw is centred on the
+        device over its observed entries (NaN = missing, set to 0); `n_obs` holds the observed counts per trait."""
+        self = cls.__new__(cls)
+        self._lib = _lib.load()
+        Y = _lib.fmat(Y_raw)
+        if Y.shape[0] != prep.n:
+            raise ValueError("X and Y must have the same number of samples.")
+        self.n, self.p, self.q = prep.n, prep.p, Y.shape[1]
+        self._ctx = ctypes.c_void_p()
+        self.n_obs = np.empty(self.q)
+        _lib.check(self._lib.aq_create_prepared(ctypes.byref(self._ctx), prep._prep, self.q, _lib.dptr(Y),
+                                                _lib.dptr(self.n_obs)))
+        self.device = prep.device
+        return self
+
+    def get_x(self):
+        X = np.empty((self.n, self.p), order="F")
+        _lib.check(self._lib.aq_get_x(self._ctx, _lib.dptr(X)))
+        return X
+
+    def get_y(self):
+        Y = np.empty((self.n, self.q), order="F")
+        _lib.check(self._lib.aq_get_y(self._ctx, _lib.dptr(Y)))
+        return Y
+
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx:
             self._lib.aq_destroy(self._ctx)
@@ -172,3 +199,75 @@ class SweepContext:
 
     def sync(self):
         _lib.check(self._lib.aq_sync(self._ctx))
+
+
+def pack_genotypes(G):
+    """n x p matrix of calls 0 / 1 / 2 -> the packed form aq_prep_geno reads: uint8 [p][ceil(n / 4)], sample i of a
+    column in bits 2 (i % 4) .. 2 (i % 4) + 1 of byte i / 4."""
+    G = np.asarray(G)
+    if G.ndim != 2:
+        raise ValueError("G must be a matrix")
+    if ((G < 0) | (G > 2) | (G != np.floor(G))).any():
+        raise ValueError("genotype calls must be 0, 1 or 2")
+    n, p = G.shape
+    nb = (n + 3) // 4
+    g = np.zeros((p, nb * 4), dtype=np.uint8)
+    g[:, :n] = G.T
+    g = g.reshape(p, nb, 4)
+    return np.ascontiguousarray(g[:, :, 0] | (g[:, :, 1] << 2) | (g[:, :, 2] << 4) | (g[:, :, 3] << 6))
+
+
+class PreparedPredictors:
+    """Predictors pre-processed on the device (aq_prep_x / aq_prep_geno): scale(X), constant and duplicated columns
+    dropped (R/prepare_atlasqtl.R:57-72).  Stands in for the standardised X matrix in the core: `.shape` is (n, p_kept)
+    and `.context(Y_raw)` creates the sweep context whose X is materialised from the raw input on the device."""
+
+    def __init__(self, X_raw=None, *, packed=None, n=None, device=0):
+        self._lib = _lib.load()
+        self._prep = ctypes.c_void_p()
+        self.device = device
+        kept = ctypes.c_int()
+        if (X_raw is None) == (packed is None):
+            raise ValueError("give either X_raw or packed genotype calls")
+        if X_raw is not None:
+            X = _lib.fmat(X_raw)
+            if X.ndim != 2:
+                raise ValueError("X must be a matrix")
+            self.n, self.p_raw = X.shape
+            _lib.check(self._lib.aq_prep_x(ctypes.byref(self._prep), ctypes.c_int(device), self.n, self.p_raw,
+                                           _lib.dptr(X), ctypes.byref(kept)))
+        else:
+            g = np.ascontiguousarray(packed, dtype=np.uint8)
+            if g.ndim != 2 or n is None or g.shape[1] < (n + 3) // 4:
+                raise ValueError("packed must be uint8 [p][>= ceil(n / 4)] and n must be given")
+            self.n, self.p_raw = int(n), g.shape[0]
+            _lib.check(self._lib.aq_prep_geno(ctypes.byref(self._prep), ctypes.c_int(device), self.n, self.p_raw,
+                                              g.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
+                                              ctypes.c_int64(g.shape[1]), ctypes.byref(kept)))
+        self.p = kept.value
+        self.status = np.empty(self.p_raw, np.uint8)
+        self.dup_of = np.empty(self.p_raw, np.int32)
+        self.mean, self.sd = np.empty(self.p_raw), np.empty(self.p_raw)
+        _lib.check(self._lib.aq_prep_result(self._prep, self.status.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
+                                            _lib.iptr(self.dup_of), _lib.dptr(self.mean), _lib.dptr(self.sd)))
+
+    @property
+    def shape(self):
+        return (self.n, self.p)
+
+    def context(self, Y_raw):
+        return SweepContext.from_prepared(self, Y_raw)
+
+    def launch_count(self):
+        return int(self._lib.aq_prep_launch_count(self._prep))
+
+    def close(self):
+        if getattr(self, "_prep", None) is not None and self._prep:
+            self._lib.aq_prep_destroy(self._prep)
+            self._prep = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -62,7 +62,7 @@ def set_hyper(q, p, eta, kappa, n0, nu, rho, t02):
 def auto_set_hyper_(Y, p, p0):
     """R/set_hyper_init.R:146-197."""
     q = Y.shape[1]
-    eta = 1 / np.median(np.var(Y, axis=0, ddof=1))
+    eta = 1 / np.median(np.nanvar(Y, axis=0, ddof=1))  # apply(Y, 2, var, na.rm = TRUE)
     if not np.isfinite(eta):
         eta = 1e3
     t02 = _solve_t02(p, p0)
@@ -104,7 +104,7 @@ def auto_set_init_(Y, p, p0, shr_fac_inv, user_seed=None):
     gam_vb = stats.norm.cdf(rng.normal(n0, s02 + t02, size=(p, q)))
     mu_beta_vb = rng.normal(size=(p, q))
     sig2_inv_vb = 1e-2
-    tau = 1 / np.median(np.var(Y, axis=0, ddof=1))
+    tau = 1 / np.median(np.nanvar(Y, axis=0, ddof=1))  # apply(Y, 2, var, na.rm = TRUE)
     if not np.isfinite(tau):
         tau = 1e3
     tau_vb = np.full(q, tau)

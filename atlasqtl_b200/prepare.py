@@ -61,3 +61,38 @@ def prepare_data_(Y, X, tol, maxit, user_seed=None, verbose=0):
     return dict(Y=np.asfortranarray(Yc), X=np.asfortranarray(Xs), bool_rmvd_x=bool_rmvd,
                 initial_colnames_X=names_after_cst, rmvd_cst_x=rmvd_cst, rmvd_coll_x=rmvd_coll, names_x=kept,
                 names_y=names_y)
+
+
+def prepare_data_device_(Y, X, tol, maxit, user_seed=None, verbose=0, *, packed_n=None, device=0):
+    """`prepare_data_` with the O(np) work on the GPU (include/atlasqtl_b200.h, aq_prep_x / aq_prep_geno): same
+    checks, same returned fields, except that "X" is a `PreparedPredictors` handle (the standardised matrix exists
+    only on the device) and "Y" is the RAW response matrix, centred on the device when the context is created.
+    X is the raw n x p matrix, or -- with packed_n = n -- packed genotype calls (`device.pack_genotypes`)."""
+    from .device import PreparedPredictors
+    Y = np.asarray(Y, dtype=np.float64)
+    if Y.ndim != 2:
+        raise ValueError("X and Y must be matrices.")
+    if not (tol > 0):
+        raise ValueError("tol must be positive.")
+    if not (maxit >= 1 and int(maxit) == maxit):
+        raise ValueError("maxit must be a natural number.")
+    n = int(packed_n) if packed_n is not None else np.shape(X)[0]
+    if Y.shape[0] != n:
+        raise ValueError("X and Y must have the same number of samples.")
+    obs = ~np.isnan(Y)
+    if obs.sum() / Y.size < 0.05:  # R/prepare_atlasqtl.R:39-40
+        raise ValueError("Too few non-NA values in matrix Y. Exit.")
+    if (obs.sum(axis=0) / n < 0.025).any():  # :42-45
+        raise ValueError("Column(s) of matrix Y have more than 97.5% missing values, and should be removed. Exit.")
+    prep = PreparedPredictors(packed=X, n=n, device=device) if packed_n is not None else PreparedPredictors(X, device=device)
+    if prep.p < 1:
+        raise ValueError("There must be at least 1 non-constant candidate predictor stored in X.")
+    names_x = [f"Cov_x_{j + 1}" for j in range(prep.p_raw)]
+    names_y = [f"Resp_{k + 1}" for k in range(Y.shape[1])]
+    rmvd_cst = [names_x[j] for j in np.flatnonzero(prep.status == 1)]
+    rmvd_coll = {}
+    for j in np.flatnonzero(prep.status == 2):
+        rmvd_coll.setdefault(names_x[prep.dup_of[j]], []).append(names_x[j])
+    return dict(Y=np.asfortranarray(Y), X=prep, bool_rmvd_x=prep.status != 0,
+                initial_colnames_X=[names_x[j] for j in np.flatnonzero(prep.status != 1)], rmvd_cst_x=rmvd_cst,
+                rmvd_coll_x=rmvd_coll, names_x=[names_x[j] for j in np.flatnonzero(prep.status == 0)], names_y=names_y)

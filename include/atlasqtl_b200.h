@@ -64,6 +64,36 @@ int aq_device_info(int device, int* sm_count, int64_t* free_bytes, int64_t* tota
 int aq_create(aq_ctx** out, int device, int n, int p, int q_local, const double* X, const double* Y);
 int aq_destroy(aq_ctx* ctx);
 
+/*
+ * Pre-processing on the device: what prepare_data_ does to X and Y before the core sees them
+ * (R/prepare_atlasqtl.R:57-83 with rm_constant_ / rm_collinear_, R/utils.R:276-343), without ever holding more than the
+ * kept, standardised columns in fp64:
+ *   X <- scale(X)                                  centre, divide by the n-1 standard deviation       (:57)
+ *   rm_constant_                                   columns that scale() turned into NaN                (:59-62)
+ *   rm_collinear_: duplicated(X, MARGIN = 2)       exact duplicates (of the standardised values), the first one is kept (:68-69)
+ *   Y <- scale(Y, center = TRUE, scale = FALSE)    column means over the observed (non-NaN) entries    (:83)
+ * aq_prep_x takes the raw n x p_raw predictors (column-major doubles); aq_prep_geno takes packed genotype calls: column j
+ * starts at geno + j * bytes_per_col, sample i is bits 2 (i % 4) .. 2 (i % 4) + 1 of byte i / 4, values 0 / 1 / 2 (3 is an
+ * error: X may not have missing values, check_structure_ R/prepare_atlasqtl.R:18).  p_kept (may be NULL) = columns left.
+ * aq_prep_result (any pointer may be NULL, all of length p_raw): status 0 kept / 1 constant / 2 duplicate, dup_of = the
+ * raw index of the kept column a duplicate equals (-1 otherwise; the names of rmvd_coll_x, R/utils.R:327-333), and the
+ * column mean and n-1 standard deviation used (0 for a constant column).
+ * aq_create_prepared: as aq_create on the prep's device with p = p_kept, X standardised on the fly from the raw input,
+ * Y_raw (n x q_local, NaN = missing) centred on the device, missing entries set to 0; n_obs (may be NULL, length q_local)
+ * = observed entries per trait.  A Y with missing entries still needs aq_set_missing.  The prep can serve several
+ * contexts (one per trait slab) and may be destroyed once they exist.
+ * aq_get_x / aq_get_y: the n x p standardised predictors / n x q_local centred responses a context holds (host, column-major).
+ */
+typedef struct aq_prep aq_prep;
+int aq_prep_x(aq_prep** out, int device, int n, int p_raw, const double* X_raw, int* p_kept);
+int aq_prep_geno(aq_prep** out, int device, int n, int p_raw, const uint8_t* geno, int64_t bytes_per_col, int* p_kept);
+int aq_prep_result(const aq_prep* prep, uint8_t* status, int32_t* dup_of, double* mean, double* sd);
+int aq_prep_destroy(aq_prep* prep);
+int64_t aq_prep_launch_count(const aq_prep* prep);
+int aq_create_prepared(aq_ctx** out, const aq_prep* prep, int q_local, const double* Y_raw, double* n_obs);
+int aq_get_x(aq_ctx* ctx, double* X);
+int aq_get_y(aq_ctx* ctx, double* Y);
+
 /* Dimensions and padded leading dimensions of the device layout (for callers that pass _dev pointers). */
 int aq_dims(const aq_ctx* ctx, int* n, int* p, int* q_local, int* p_pad, int* q_pad);
 
