@@ -109,6 +109,10 @@ struct aq_ctx {
     unsigned long long* mask = nullptr;
     double *xnsq = nullptr, *n_obs = nullptr, *mis_out = nullptr;
     bool has_mis = false;
+    double* rowpart = nullptr;      // [rowpart_cap][p_pad] per-tile row sums of gam W + I0 left by the last aq_sweep
+    int rowpart_cap = 0, rowpart_rows = 0;   // rows allocated / rows the last sweep wrote (0: not valid)
+    int rowpart_k_tail = -1;                 // first trait NOT covered by those rows (-1: all are)
+    bool rowpart_tried = false;
     double* sel_partial = nullptr;  // scratch of the selection kernels: 2 x kSelBlocks partials + 2 results
     std::vector<int32_t> order, order_pad;
     std::vector<double> hbuf;   // pinned-size-agnostic host scratch
@@ -199,10 +203,36 @@ int launch_sweep_cfg(aq_ctx* c, const SweepParams& P) {
             n_tail = tail_tiles;
         }
     }
+    SweepParams Pm = P, Pt = P;
+    c->rowpart_rows = 0;
+    if (P.mode == 0) {
+        // per-tile row sums of gam W + I0 ride along with the sweep (aq_rowsums_zpart reduces them); without the scratch
+        // buffer the streaming row-sum kernel is used instead
+        if (!c->rowpart && !c->rowpart_tried) {
+            c->rowpart_tried = true;
+            c->rowpart_cap = ntiles + G;
+            if (cudaMalloc((void**)&c->rowpart, sizeof(double) * (size_t)c->rowpart_cap * c->p_pad) != cudaSuccess) {
+                cudaGetLastError();
+                c->rowpart = nullptr;
+            }
+        }
+        // (measured: +0.5-1 % on a tensor-bound tile, +2.5 % on the chain-bound 8-trait tail tiles and cluster tiles, whose
+        // helper warp sits closer to the serial path; the streaming pass costs 24 B per update, i.e. 2-6 % of a sweep for
+        // n <= 1008 and < 1 % beyond.  So: full-size single-CTA tiles only; the tail's traits get one streamed extra row.)
+        if (c->rowpart && !CL && n_main > 0 && n_main + 1 <= c->rowpart_cap && !std::getenv("AQ_NO_ROWPART")) {
+            Pm.rowpart = c->rowpart;
+            Pm.rowpart_base = 0;
+            c->rowpart_rows = n_main;
+            c->rowpart_k_tail = n_tail > 0 ? k_tail : -1;
+        }
+    }
     AQ_CUDA(cudaEventRecord(c->ev0, c->stream));
-    rc = launch_sweep_t<Main>(c, P, n_main, 0, nullptr);
-    if (rc == AQ_OK && n_tail > 0) rc = launch_sweep_t<Tail>(c, P, n_tail, k_tail, nullptr);
-    if (rc != AQ_OK) return rc;
+    rc = launch_sweep_t<Main>(c, Pm, n_main, 0, nullptr);
+    if (rc == AQ_OK && n_tail > 0) rc = launch_sweep_t<Tail>(c, Pt, n_tail, k_tail, nullptr);
+    if (rc != AQ_OK) {
+        c->rowpart_rows = 0;
+        return rc;
+    }
     AQ_CUDA(cudaEventRecord(c->ev1, c->stream));
     return AQ_OK;
 }
@@ -244,6 +274,9 @@ int launch_sweep(aq_ctx* c, int mode, double cc, double log_sig2_inv) {
     P.cs_b2 = c->ovec + 2 * (size_t)c->q_pad;
     P.rsq = c->ovec + 3 * (size_t)c->q_pad;
     P.cs_z = c->ovec + 4 * (size_t)c->q_pad;
+    P.rowpart = nullptr;
+    P.rowpart_base = 0;
+    P.p_pad = c->p_pad;
     P.mode = mode;
     P.timing = nullptr;
 #ifdef AQ_TIMING
@@ -263,6 +296,7 @@ int launch_sweep(aq_ctx* c, int mode, double cc, double log_sig2_inv) {
 
 int upload_pxq(aq_ctx* c, const double* host, double* dev) {
     // host: p x q column-major.  Staged in chunks of stage_cols traits, transposed on the device.
+    c->rowpart_rows = 0;  // gam or a table changes: the last sweep's row-sum partials no longer describe the state
     for (int k0 = 0; k0 < c->q; k0 += c->stage_cols) {
         const int kc = std::min(c->stage_cols, c->q - k0);
         AQ_CUDA(cudaMemcpyAsync(c->stage, host + (size_t)k0 * c->p, sizeof(double) * (size_t)kc * c->p,
@@ -381,7 +415,7 @@ int aq_destroy(aq_ctx* c) {
         if (b) cudaFree(b);
     if (c->order_dev) cudaFree(c->order_dev);
     if (c->mask) cudaFree(c->mask);
-    for (double* b : {c->xnsq, c->n_obs, c->mis_out, c->sel_partial})
+    for (double* b : {c->xnsq, c->n_obs, c->mis_out, c->sel_partial, c->rowpart})
         if (b) cudaFree(b);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -813,6 +847,7 @@ int aq_refresh_tables(aq_ctx* c, const double* theta_vb, const double* zeta_vb, 
     if (!(c_next > 0.0)) return fail(AQ_EINVAL, "aq_refresh_tables: c_next must be positive");
     if (elbo_b_part && !c->have_state) return fail(AQ_ESTATE, "aq_refresh_tables: ELBO part needs a state");
     AQ_CUDA(cudaSetDevice(c->device));
+    c->rowpart_rows = 0;  // W / I0 change
     AQ_CUDA(cudaMemcpyAsync(c->theta, theta_vb, sizeof(double) * c->p, cudaMemcpyHostToDevice, c->stream));
     AQ_CUDA(cudaMemcpyAsync(c->zeta, zeta_vb, sizeof(double) * c->q, cudaMemcpyHostToDevice, c->stream));
     const int c_is_one = std::fabs(c_next - 1.0) < 1.5e-8;  // isTRUE(all.equal(c, 1)), R/update_vb.R:219
@@ -863,7 +898,19 @@ int aq_rowsums_zpart_dev(aq_ctx* c, double** rowsum_zpart_dev) {
     if (!c->have_state || !c->have_tables) return fail(AQ_ESTATE, "aq_rowsums_zpart before state/tables");
     AQ_CUDA(cudaSetDevice(c->device));
     AQ_CUDA(cudaEventRecord(c->evr0, c->stream));
-    rowsums_kernel<<<(c->p + 7) / 8, 256, 0, c->stream>>>(c->gam, c->wtab, c->i0tab, c->p, c->q, c->q_pad, c->rowsum);
+    if (c->rowpart_rows > 0) {  // the last sweep left per-tile partial sums: no second pass over the p x q arrays
+        int rows = c->rowpart_rows;
+        if (c->rowpart_k_tail >= 0) {  // traits swept by the 8-trait tail launch: streamed into one more row
+            const int kt = c->rowpart_k_tail;
+            rowsums_kernel<<<(c->p + 7) / 8, 256, 0, c->stream>>>(c->gam + kt, c->wtab + kt, c->i0tab + kt, c->p, c->q - kt,
+                                                                  c->q_pad, c->rowpart + (size_t)rows * c->p_pad);
+            AQ_CUDA(cudaGetLastError());
+            c->launches++;
+            ++rows;
+        }
+        rowpart_reduce_kernel<<<(c->p + 31) / 32, dim3(32, 8), 0, c->stream>>>(c->rowpart, rows, c->p, c->p_pad, c->rowsum);
+    } else
+        rowsums_kernel<<<(c->p + 7) / 8, 256, 0, c->stream>>>(c->gam, c->wtab, c->i0tab, c->p, c->q, c->q_pad, c->rowsum);
     AQ_CUDA(cudaGetLastError());
     c->launches++;
     AQ_CUDA(cudaEventRecord(c->evr1, c->stream));
@@ -908,6 +955,7 @@ int launch_mis(aq_ctx* c, int mode, double cc, double log_sig2_inv, double sig2_
     P.sig2_inv = sig2_inv;
     P.out = c->mis_out;
     P.mode = mode;
+    c->rowpart_rows = 0;
     const int warps = 4, grid = (c->q + warps - 1) / warps;
     const int M = (c->n + 31) / 32;
     AQ_CUDA(cudaEventRecord(c->ev0, c->stream));

@@ -212,4 +212,33 @@ __global__ void __launch_bounds__(256) rowsums_kernel(const double* __restrict__
     if (lane == 0) rowsum[j] = s;
 }
 
+// rowsum[j] = sum over the sweep's trait tiles of their partial row sums (rowpart [nrows][p_pad], written by the helper
+// warps of the sweep kernel): 0.5 GB instead of the 24 GB of the three p x q arrays at C2.  Block = 32 SNPs x 8 row
+// lanes; fixed order.
+__global__ void __launch_bounds__(256) rowpart_reduce_kernel(const double* __restrict__ rowpart, int nrows, int p, int p_pad,
+                                                             double* __restrict__ rowsum) {
+    __shared__ double red[8][33];
+    const int j = blockIdx.x * 32 + threadIdx.x;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (j < p) {
+        const double* col = rowpart + j;
+        int r = threadIdx.y;
+        for (; r + 24 < nrows; r += 32) {
+            s0 += col[(size_t)r * p_pad];
+            s1 += col[(size_t)(r + 8) * p_pad];
+            s2 += col[(size_t)(r + 16) * p_pad];
+            s3 += col[(size_t)(r + 24) * p_pad];
+        }
+        for (; r < nrows; r += 8) s0 += col[(size_t)r * p_pad];
+    }
+    red[threadIdx.y][threadIdx.x] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (threadIdx.y == 0 && j < p) {
+        double s = 0.0;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) s += red[y][threadIdx.x];
+        rowsum[j] = s;
+    }
+}
+
 }  // namespace aq

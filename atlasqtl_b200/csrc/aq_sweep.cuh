@@ -65,6 +65,9 @@ struct SweepParams {
     double* cs_b2;
     double* rsq;
     double* cs_z;
+    double* rowpart;        // [rowpart_base + tile][p_pad] this tile's part of rowsum_j = sum_k gam W + I0 (NULL: not wanted)
+    int rowpart_base;       // first row of this launch in rowpart
+    int p_pad;
     int mode;               // 0: sweep;  1: build residual (R -= X beta) + sums from the loaded state
     long long* timing;      // development only (-DAQ_TIMING): per-section cycle sums of the chain warp
 };
@@ -88,7 +91,7 @@ struct SweepCfg {
     static constexpr size_t kSpartDoubles = (size_t)WS * kT * kSps;      // [WS][kT][kSps], single-buffered (sfree barrier)
     // who sums the split-K partials of S: the chain warp itself (single CTA: one hop less between the tensor work and the
     // recurrence), or the helper warp (clusters: the wait for the other CTAs' slices stays off the serial path)
-    static constexpr bool kChainSums = !kCl;
+    static constexpr bool kChainSums = !kCl && MT > 1;
     static constexpr size_t kSsumDoubles = kChainSums ? 0 : (size_t)2 * kT * kSps;  // [2][kT][kSps] summed S tile for the chain
     static constexpr size_t kDbufDoubles = (size_t)2 * kT * kBlk;
     static constexpr size_t kRsqDoubles = (size_t)WS * kT;
@@ -109,6 +112,28 @@ struct SweepCfg {
     static_assert(kXS % 16 == 8, "row stride must be 8 mod 16 doubles");
     static_assert(kSmemBytes <= 232448, "shared memory budget (227 KB)");
 };
+
+// Sums of N values per lane over a group of G consecutive lanes (G = 4 N), by recursive halving: at every step a lane
+// hands half of its values to its partner and keeps the other half.  On return v[0] of lane L is the group total of value
+// slot_of(L) = the N-ary digit string of L's upper lane bits (see the caller); fixed order, deterministic.
+template <int N>
+__device__ __forceinline__ void group_sums(double (&v)[N], int lane, int top_bit) {
+    if constexpr (N > 1) {
+        const bool up = (lane & top_bit) != 0;
+        double w[N / 2];
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) {
+            const double send = up ? v[i] : v[i + N / 2];
+            const double keep = up ? v[i + N / 2] : v[i];
+            w[i] = keep + __shfl_xor_sync(0xffffffffu, send, top_bit);
+        }
+        group_sums<N / 2>(w, lane, top_bit >> 1);
+        v[0] = w[0];
+    } else {
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+    }
+}
 
 // S = X_b' R of one block: sums this CTA's WS split-K partials and, on a cluster leader, the tiles the other CTAs shipped.
 // Lane layout: trait `tsum`, and with <= 16 traits per tile the two half-warps split the partials of a trait between them.
@@ -489,6 +514,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 const double sig2 = P.sig2_beta[k];
                 const double cst = -(P.log_tau[k] + P.log_sig2_inv + log(sig2)) / 2;  // src/coreLoop.cpp:56
                 double sg = 0.0, sgm2 = 0.0, sb2 = 0.0, sz = 0.0;
+                double* rowrow = P.rowpart ? P.rowpart + (size_t)(P.rowpart_base + tile) * P.p_pad : nullptr;
                 // asynchronous copies (LDGSTS) of this lane's gam / mu / D / W / I0 elements of block `blk` into the staging
                 // buffer: issued a whole block ahead, so neither preparing a block nor finishing it ever waits on HBM or L2
                 auto stage_rows = [&](int blk) {
@@ -555,23 +581,38 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     mbar_wait(&dready[g & 1], (uint32_t)((g >> 1) & 1));
                     AQ_T(8);
                     const double* io = iobuf + (size_t)(g & 1) * kBlk * 2 * kT;
+                    double zrow[kTP];
 #pragma unroll
                     for (int i = 0; i < kTP; ++i) {
                         const int t = t0 + i;
                         const double gm = io[(t * 2 + 0) * kT + tls];
                         const double m = io[(t * 2 + 1) * kT + tls];
+                        zrow[i] = 0.0;
                         if (idc[i] >= 0) {
                             const double bn = gm * m;  // :79
+                            const double z = fma(gm, ww[i], ii[i]);
                             sg += gm;
                             sgm2 = fma(bn, m, sgm2);
                             sb2 = fma(bn, bn, sb2);
-                            sz += fma(gm, ww[i], ii[i]);
+                            sz += z;
                             if (valid) {
                                 const size_t off = (size_t)idc[i] * P.q_pad + k;
                                 P.gam[off] = gm;
                                 P.mu[off] = m;
+                                zrow[i] = z;
                             }
                         }
+                    }
+                    if (P.rowpart) {
+                        // this tile's share of rowSums(Z) (update_theta_vb_, R/update_vb.R:179): the products are here anyway,
+                        // so the p x q arrays are not read a second time for them.  Lanes of a half-warp (a warp if kT > 16)
+                        // hold the traits; after the halving sums lane L owns SNP slot (L >> 2) & (kTP - 1) of its half.
+                        group_sums<kTP>(zrow, lane, kH == 2 ? 8 : 16);
+                        const int slot = (lane >> 2) & (kTP - 1);
+                        int ids = idc[0];
+#pragma unroll
+                        for (int i = 1; i < kTP; ++i) ids = slot == i ? idc[i] : ids;
+                        if ((lane & 3) == 0 && ids >= 0) rowrow[ids] = zrow[0];
                     }
                     AQ_T(9);
                 };

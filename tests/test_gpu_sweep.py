@@ -50,6 +50,11 @@ def zparts(si, gam):
     (200, 300, 200, 0.8, "reference", True),
     (500, 203, 70, 1.0, "primal", True),
     (1000, 120, 50, 0.5, "primal", False),
+    # one full round of the persistent grid (148 tiles) + a tail launch: the row sums come from the per-tile partials
+    # the helper warps leave (main launch) plus one streamed row (tail traits)
+    (1000, 21, 2500, 0.5, "primal", True),    # 16-trait tiles, 17 tail tiles of 8
+    (100, 24, 4776, 0.7, "primal", True),     # 32-trait tiles (one trait per helper lane), 5 tail tiles
+    (600, 19, 3552 + 3, 1.0, "primal", False),  # 24-trait tiles, q not a multiple of 8
 ])
 def test_single_sweep_parity(oracle_built, n, p, q, c, form, shuffle):
     from atlasqtl_b200.device import SweepContext
