@@ -121,6 +121,23 @@ __device__ __forceinline__ NormalPoint normal_point(double u, bool want_logs, bo
     return o;
 }
 
+// The same point when only the log-odds of the tail are wanted (no ELBO on this iteration): one log instead of log + log1p,
+// log(Q / (1 - Q)) = log(E / (2 (1 - Q))) - u^2 / 2, and the reciprocal of 1 - Q is shared with phi / (1 - Q).
+// (exp underflows beyond |u| = 38.6: Q = 0 there and the expression degrades to log(E / 2) - u^2 / 2, still exact.)
+__device__ __forceinline__ double normal_point_logodds(double u, bool want_ratios, double& r_tail, double& r_body) {
+    const double kRs2 = 0.70710678118654752440, kSqrt2OverPi = 0.79788456080286535588, kInvSqrt2Pi = 0.39894228040143267794;
+    const double a = fabs(u) * kRs2;
+    const double E = erfcx(a);
+    const double e2 = exp(-0.5 * u * u);
+    const double Q = 0.5 * E * e2;
+    const double inv = 1.0 / (1.0 - Q);
+    if (want_ratios) {
+        r_tail = kSqrt2OverPi / E;
+        r_body = kInvSqrt2Pi * e2 * inv;
+    }
+    return log(0.5 * E * inv) - 0.5 * u * u;
+}
+
 __global__ void __launch_bounds__(256) tables_kernel(const double* __restrict__ theta, const double* __restrict__ zeta, int p,
                                                      int q, int q_pad, double sqrt_c, int c_is_one,
                                                      const double* __restrict__ gam, double* __restrict__ dtab,
@@ -138,11 +155,18 @@ __global__ void __launch_bounds__(256) tables_kernel(const double* __restrict__ 
             if (j >= p) break;
             const size_t off = (size_t)j * q_pad + k;
             const double u = theta[j] + zk;
-            const NormalPoint nu = normal_point(u, true, c_is_one != 0);
-            const double lp = (u >= 0.0) ? nu.log_body : nu.log_tail;  // log Phi(u)
-            const double lq = (u >= 0.0) ? nu.log_tail : nu.log_body;  // log(1 - Phi(u))
-            dtab[off] = lq - lp;
-            double U = u, r_tail = nu.r_tail, r_body = nu.r_body;
+            double lp = 0.0, lq = 0.0, U = u, r_tail = 0.0, r_body = 0.0;
+            if (want_elbo) {
+                const NormalPoint nu = normal_point(u, true, c_is_one != 0);
+                lp = (u >= 0.0) ? nu.log_body : nu.log_tail;  // log Phi(u)
+                lq = (u >= 0.0) ? nu.log_tail : nu.log_body;  // log(1 - Phi(u))
+                dtab[off] = lq - lp;
+                r_tail = nu.r_tail;
+                r_body = nu.r_body;
+            } else {
+                const double lo = normal_point_logodds(u, c_is_one != 0, r_tail, r_body);  // log(tail / body)
+                dtab[off] = (u >= 0.0) ? lo : -lo;
+            }
             if (!c_is_one) {  // update_Z_ evaluates the CDFs at sqrt(c) (theta + zeta) while annealing (R/update_vb.R:219-224)
                 U = sqrt_c * u;
                 const NormalPoint nU = normal_point(U, false, true);
