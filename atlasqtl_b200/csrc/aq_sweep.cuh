@@ -599,11 +599,11 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                                 const size_t off = (size_t)idc[i] * P.q_pad + k;
                                 P.gam[off] = gm;
                                 P.mu[off] = m;
-                                zrow[i] = z;
+                                if (!kCl) zrow[i] = z;
                             }
                         }
                     }
-                    if (P.rowpart) {
+                    if (!kCl && P.rowpart) {  // (never requested from a clustered launch)
                         // this tile's share of rowSums(Z) (update_theta_vb_, R/update_vb.R:179): the products are here anyway,
                         // so the p x q arrays are not read a second time for them.  Lanes of a half-warp (a warp if kT > 16)
                         // hold the traits; after the halving sums lane L owns SNP slot (L >> 2) & (kTP - 1) of its half.
