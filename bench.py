@@ -274,6 +274,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         from atlasqtl_b200.dist import TorchComm
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout: keep stdout to the ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         comm = TorchComm()
     k0, k1 = slab_bounds(q, rank, world)

@@ -150,6 +150,59 @@ SEXP _atlasqtl_aq_sweep_mis(SEXP ptr, SEXP c, SEXP log_sig2_inv_vb, SEXP sig2_in
   return res;
 }
 
+/* prepare_data_ on the device (R/prepare_atlasqtl.R:57-83): X raw n x p double matrix, or a raw vector of packed
+ * 2-bit calls (bytes_per_col * p bytes) with n given.  Returns list(prep = <external pointer>, status, dup_of, mean, sd). */
+static void prep_finalizer(SEXP ptr) {
+  aq_prep* P = (aq_prep*)R_ExternalPtrAddr(ptr);
+  if (P) { aq_prep_destroy(P); R_ClearExternalPtr(ptr); }
+}
+static SEXP prep_result(aq_prep* P, int p_raw) {
+  static const char* names[] = {"prep", "status", "dup_of", "mean", "sd"};
+  SEXP res = PROTECT(Rf_allocVector(VECSXP, 5)), nm = PROTECT(Rf_allocVector(STRSXP, 5));
+  SEXP ptr = PROTECT(R_MakeExternalPtr(P, R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(ptr, prep_finalizer, TRUE);
+  SEXP status = PROTECT(Rf_allocVector(RAWSXP, p_raw)), dup = PROTECT(Rf_allocVector(INTSXP, p_raw));
+  SEXP mean = PROTECT(Rf_allocVector(REALSXP, p_raw)), sd = PROTECT(Rf_allocVector(REALSXP, p_raw));
+  int rc = aq_prep_result(P, RAW(status), (int32_t*)INTEGER(dup), REAL(mean), REAL(sd));
+  SET_VECTOR_ELT(res, 0, ptr); SET_VECTOR_ELT(res, 1, status); SET_VECTOR_ELT(res, 2, dup);
+  SET_VECTOR_ELT(res, 3, mean); SET_VECTOR_ELT(res, 4, sd);
+  for (int i = 0; i < 5; ++i) SET_STRING_ELT(nm, i, Rf_mkChar(names[i]));
+  Rf_setAttrib(res, R_NamesSymbol, nm);
+  UNPROTECT(7);
+  check(rc);
+  return res;
+}
+SEXP _atlasqtl_aq_prep_x(SEXP X, SEXP device) {
+  if (!Rf_isReal(X) || !Rf_isMatrix(X)) Rf_error("X must be a double matrix");
+  aq_prep* P = NULL;
+  check(aq_prep_x(&P, Rf_asInteger(device), Rf_nrows(X), Rf_ncols(X), REAL(X), NULL));
+  return prep_result(P, Rf_ncols(X));
+}
+SEXP _atlasqtl_aq_prep_geno(SEXP geno, SEXP n, SEXP p, SEXP bytes_per_col, SEXP device) {
+  if (TYPEOF(geno) != RAWSXP) Rf_error("geno must be a raw vector");
+  int pp = Rf_asInteger(p);
+  double bpc = Rf_asReal(bytes_per_col);
+  if ((double)XLENGTH(geno) < bpc * pp) Rf_error("geno is shorter than bytes_per_col * p");
+  aq_prep* P = NULL;
+  check(aq_prep_geno(&P, Rf_asInteger(device), Rf_asInteger(n), pp, RAW(geno), (int64_t)bpc, NULL));
+  return prep_result(P, pp);
+}
+/* context over the kept columns; Y raw (NA = missing).  Returns the context with attribute "n_obs" = colSums(!is.na(Y)) */
+SEXP _atlasqtl_aq_create_prepared(SEXP prep, SEXP Y) {
+  aq_prep* P = (aq_prep*)R_ExternalPtrAddr(prep);
+  if (!P) Rf_error("atlasqtl_b200: prep already destroyed");
+  if (!Rf_isReal(Y) || !Rf_isMatrix(Y)) Rf_error("Y must be a double matrix");
+  SEXP n_obs = PROTECT(Rf_allocVector(REALSXP, Rf_ncols(Y)));
+  aq_ctx* c = NULL;
+  int rc = aq_create_prepared(&c, P, Rf_ncols(Y), REAL(Y), REAL(n_obs));   /* NA_real_ is a NaN: read as missing */
+  if (rc != AQ_OK) { UNPROTECT(1); check(rc); }
+  SEXP ptr = PROTECT(R_MakeExternalPtr(c, R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(ptr, ctx_finalizer, TRUE);
+  Rf_setAttrib(ptr, Rf_install("n_obs"), n_obs);
+  UNPROTECT(2);
+  return ptr;
+}
+
 /* Stateless drop-in with the reference's exact 15 arguments (src/RcppExports.cpp:17). */
 SEXP _atlasqtl_coreDualLoop(SEXP cp_X, SEXP cp_Y_X, SEXP gam_vb, SEXP log_Phi, SEXP log_1_min_Phi, SEXP log_sig2_inv_vb,
                             SEXP log_tau_vb, SEXP m1_beta, SEXP cp_betaX_X, SEXP mu_beta_vb, SEXP sig2_beta_vb,
@@ -174,6 +227,9 @@ static const R_CallMethodDef CallEntries[] = {
     {"_atlasqtl_aq_set_missing", (DL_FUNC)&_atlasqtl_aq_set_missing, 2},
     {"_atlasqtl_aq_set_state_mis", (DL_FUNC)&_atlasqtl_aq_set_state_mis, 3},
     {"_atlasqtl_aq_sweep_mis", (DL_FUNC)&_atlasqtl_aq_sweep_mis, 6},
+    {"_atlasqtl_aq_prep_x", (DL_FUNC)&_atlasqtl_aq_prep_x, 2},
+    {"_atlasqtl_aq_prep_geno", (DL_FUNC)&_atlasqtl_aq_prep_geno, 5},
+    {"_atlasqtl_aq_create_prepared", (DL_FUNC)&_atlasqtl_aq_create_prepared, 2},
     {"_atlasqtl_coreDualLoop", (DL_FUNC)&_atlasqtl_coreDualLoop, 15},
     {NULL, NULL, 0}};
 
