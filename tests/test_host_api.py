@@ -70,3 +70,54 @@ def test_assign_bfdr_matches_definition_and_ties_are_stable():
         assert abs(fdr.flatten(order="F")[idx] - expect) < 1e-15
     sel = summarise.selected_pairs(ppi, 0.55)
     assert {tuple(x) for x in sel} == {(0, 0), (1, 0), (1, 2)}
+
+
+def test_pack_genotypes_layout():
+    """Packed calls as aq_prep_geno reads them: sample i of a column = bits 2 (i % 4) .. 2 (i % 4) + 1 of byte i / 4."""
+    from atlasqtl_b200.device import pack_genotypes
+    rng = np.random.default_rng(1)
+    for n in (1, 4, 7, 50):
+        G = rng.integers(0, 3, size=(n, 9))
+        g = pack_genotypes(G)
+        assert g.dtype == np.uint8 and g.shape == (9, (n + 3) // 4)
+        back = np.stack([(g[:, i // 4] >> (2 * (i % 4))) & 3 for i in range(n)])
+        assert np.array_equal(back, G)
+        if n % 4:  # padding samples of the last byte are call 0
+            assert ((g[:, -1] >> (2 * (n % 4))) == 0).all()
+    for bad in (np.array([[0, 3]]), np.array([[0.5, 1.0]]), np.array([[-1, 0]])):
+        with pytest.raises(ValueError):
+            pack_genotypes(bad)
+
+
+def test_prepare_data_device_checks_before_touching_the_gpu():
+    """Argument checks of prepare_data_ (R/prepare_atlasqtl.R:11-45) come first; without a GPU the device path then
+    raises instead of falling back to the host implementation."""
+    import torch
+
+    from atlasqtl_b200 import _lib
+    rng = np.random.default_rng(2)
+    G = rng.binomial(2, 0.3, size=(50, 6)).astype(float)
+    Y = rng.normal(size=(50, 3))
+    with pytest.raises(ValueError, match="same number of samples"):
+        prepare.prepare_data_device_(Y[:30], G, 0.1, 10)
+    with pytest.raises(ValueError, match="tol"):
+        prepare.prepare_data_device_(Y, G, 0.0, 10)
+    Yn = Y.copy()
+    Yn[1:, 1] = np.nan
+    with pytest.raises(ValueError, match="97.5% missing"):
+        prepare.prepare_data_device_(Yn, G, 0.1, 10)
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.AtlasqtlB200Error):
+            prepare.prepare_data_device_(Y, G, 0.1, 10)
+
+
+def test_hyper_init_ignore_missing_responses():
+    """eta / tau come from apply(Y, 2, var, na.rm = TRUE) (R/set_hyper_init.R:153)."""
+    rng = np.random.default_rng(3)
+    Y = rng.normal(size=(60, 5))
+    Yn = Y.copy()
+    Yn[::7, 2] = np.nan
+    h = hyper_init.auto_set_hyper_(Yn, 20, (2, 10))
+    assert np.isfinite(h["eta"]).all()
+    expect = 1 / np.median([np.var(Yn[~np.isnan(Yn[:, k]), k], ddof=1) for k in range(5)])
+    np.testing.assert_allclose(np.atleast_1d(h["eta"])[0], expect, rtol=1e-12)
