@@ -205,7 +205,7 @@ int launch_sweep_cfg(aq_ctx* c, const SweepParams& P) {
     }
     SweepParams Pm = P, Pt = P;
     c->rowpart_rows = 0;
-    if (P.mode == 0) {
+    if (P.mode == 0 && !CL) {
         // per-tile row sums of gam W + I0 ride along with the sweep (aq_rowsums_zpart reduces them); without the scratch
         // buffer the streaming row-sum kernel is used instead
         if (!c->rowpart && !c->rowpart_tried) {
@@ -219,7 +219,7 @@ int launch_sweep_cfg(aq_ctx* c, const SweepParams& P) {
         // (measured: +0.5-1 % on a tensor-bound tile, +2.5 % on the chain-bound 8-trait tail tiles and cluster tiles, whose
         // helper warp sits closer to the serial path; the streaming pass costs 24 B per update, i.e. 2-6 % of a sweep for
         // n <= 1008 and < 1 % beyond.  So: full-size single-CTA tiles only; the tail's traits get one streamed extra row.)
-        if (c->rowpart && !CL && n_main > 0 && n_main + 1 <= c->rowpart_cap && !std::getenv("AQ_NO_ROWPART")) {
+        if (c->rowpart && n_main > 0 && n_main + 1 <= c->rowpart_cap && !std::getenv("AQ_NO_ROWPART")) {
             Pm.rowpart = c->rowpart;
             Pm.rowpart_base = 0;
             c->rowpart_rows = n_main;

@@ -274,8 +274,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
         from atlasqtl_b200.dist import TorchComm
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout: keep stdout to the ONE JSON line
+        # NCCL writes its debug output (the version banner at NCCL_DEBUG=VERSION / WARN) to stdout: send it to stderr so
+        # that stdout carries the ONE JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         comm = TorchComm()
     k0, k1 = slab_bounds(q, rank, world)
