@@ -15,6 +15,7 @@ Traits are independent inside a sweep, so several processes can each own a slab 
 partial sums; they go through `comm.allreduce_sum` (NCCL via torch.distributed, see dist.py).
 """
 import math
+import time
 import os
 from concurrent.futures import ThreadPoolExecutor
 
@@ -324,6 +325,13 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
             it += 1
             if iter_hook is not None:
                 iter_hook(it, ctx)
+            _t = [time.perf_counter()]
+            seg = {}
+
+            def _lap(name):  # host wall-clock per segment of the iteration (rec["host_ms"], for profiling the loop itself)
+                t1 = time.perf_counter()
+                seg[name] = seg.get(name, 0.0) + 1e3 * (t1 - _t[0])
+                _t[0] = t1
             if verbose != 0 and comm.rank == 0 and (it == 1 or it % max(5, batch_conv) == 0):
                 print(f"Iteration {it}... ")
 
@@ -352,6 +360,7 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
                 return L_, Q_, 1 / (Q_ * L_) - 1  # :254
             hs_future = _background().submit(_hs_scale)
 
+            _lap("pre")
             # ---- the sweep (:167-170) with the fused reductions
             if mis_pat is None:
                 sums = ctx.sweep(c, log_sig2_inv_vb, tau_vb, log_tau_vb, sig2_beta_vb)
@@ -360,10 +369,13 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
                 sums["colsum_m2"] = sums["colsum_gam_mu2"] + sums["colsum_sig2b_gam"]  # update_m2_beta_ with p x q sig2_beta_vb
                 sums["colsum_xn_m2"] = sums["colsum_xn_gam_mu2"] + sums["colsum_xn_sig2b_gam"]
             sig2_beta_for_m2 = sig2_beta_vb
+            _lap("sweep")
             colsum_m2 = m2_of(sums)  # :235
             rows = ctx.rowsums_zpart()
+            _lap("rowsums")
             glob = comm.allreduce_sum(np.concatenate([rows, [sums["colsum_gam"].sum(), np.dot(tau_vb, colsum_m2)]]))
             rowsum_zpart, sum_gam, tau_dot_m2 = glob[:p], float(glob[p]), float(glob[p + 1])
+            _lap("allreduce")
 
             sqrt_c = 1.0 if abs(c - 1) < ALL_EQUAL_TOL else math.sqrt(c)  # R/update_vb.R:219-229
             rowsums_Z = rowsum_zpart / sqrt_c + q_total * theta_vb + sum_zeta  # :237
@@ -371,6 +383,7 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
 
             rho_xi_inv_vb = c_s * (A2_inv + sig02_inv_vb)  # :242
             L_vb, Q_new, lam2_inv_vb = hs_future.result()
+            _lap("hs_wait")
             if Q_new is not None:
                 Q_app = Q_new
             xi_inv_vb = nu_xi_inv_vb / rho_xi_inv_vb  # :276
@@ -401,8 +414,10 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
             else:
                 want_elbo = it <= it_init + 1 or it % batch_conv == 0 or it % batch_conv == 1  # :342
 
+            _lap("theta_zeta")
             # theta / zeta changed: refresh D, W, I0 for the next sweep (:293-295), ELBO-B part on demand
             elbo_b_dev = ctx.refresh_tables(theta_vb, zeta_vb, c_next=c, want_elbo=want_elbo)
+            _lap("tables")
             sum_zeta_local = zeta_vb.sum()
             if hasattr(ctx, "last_ms"):
                 rec["tables_ms"] = ctx.last_ms(2)
@@ -461,9 +476,11 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
                     batch_conv = batch_conv_sched[ind_batch_conv - 1]
             else:
                 sum_zeta = float(comm.allreduce_sum(np.array([sum_zeta_local]))[0])
+            _lap("elbo")
             if trace is not None:
                 rec["c_next"] = c
                 rec["c"] = c_prev
+                rec["host_ms"] = seg
                 trace.append(rec)
             checkpoint_(it, checkpoint_path, ctx, theta_vb, zeta_vb, converged, lb_new, lb_old, lam2_inv_vb, sig02_inv_vb,
                         comm=comm, rate=checkpoint_rate,

@@ -316,6 +316,10 @@ def main():
                                          slab=(k0, k1), ctx=ctx, trace=trace, iter_hook=hook)
         clocks = sampler.stop() if rank == 0 else None
         timed = [r for r in trace if W < r["it"] <= W + K]
+        if rank == 0 and timed and "host_ms" in timed[0]:
+            keys = list(timed[0]["host_ms"])
+            log("[host wall-clock per step, ms] " + ", ".join(
+                f"{k}={np.mean([r['host_ms'].get(k, 0.0) for r in timed]):.2f}" for k in keys))
         dev_ms = sum(r["sweep_ms"] + r["rows_ms"] + r["tables_ms"] for r in timed)
         sweep_ms = float(np.mean([r["sweep_ms"] for r in timed]))
         wall_ms = 1e3 * (marks["t1"] - marks["t0"])
