@@ -14,6 +14,8 @@ Contents
 ``native.py``       ctypes loaders for both libraries.
 ``vb_oracle.py``    NumPy/SciPy restatement of the R outer loop and the ELBO
                     (``R/atlasqtl_global_local_core.R``, ``R/update_vb.R``, ``R/elbo.R``).
+``prepare_oracle.py``  literal restatement of ``prepare_data_``'s X / Y work (``scale``, ``rm_constant_``,
+                    ``rm_collinear_``; ``R/prepare_atlasqtl.R:57-83``, ``R/utils.R:276-343``).
 
 Parity status: the sweep is pinned against the reference's own C++ (``_ref``); the outer
 loop is a restatement with no R available to run -- "parity unpinned" for that part, see

@@ -1,5 +1,6 @@
-"""GPU: pre-processing on the device (aq_prep_x / aq_prep_geno / aq_create_prepared) against the host mirror of
-prepare_data_ (R/prepare_atlasqtl.R:57-83, rm_constant_ / rm_collinear_ R/utils.R:276-343).
+"""GPU: pre-processing on the device (aq_prep_x / aq_prep_geno / aq_create_prepared) against the CPU oracle's literal
+restatement of prepare_data_ (oracle/prepare_oracle.py; R/prepare_atlasqtl.R:57-83, rm_constant_ / rm_collinear_
+R/utils.R:276-343) and against the package's host mirror of the same function.
 
 Integer outputs (which columns are constant / duplicated, and of which kept column) must match exactly; the
 standardised X and the centred Y to 1e-13 absolute (values are O(1); the summation order of a mean differs)."""
@@ -35,6 +36,18 @@ def raw_problem(n, p, q, seed=5, continuous=True, na_frac=0.0):
     return np.asfortranarray(G), np.asfortranarray(Y)
 
 
+def check_against_oracle(G, Y_raw, prep, ctx):
+    """Against the literal restatement of R's scale / rm_constant_ / rm_collinear_ (oracle/prepare_oracle.py)."""
+    from oracle import prepare_oracle
+    o = prepare_oracle.prepare_data_(Y_raw, G)
+    assert np.array_equal(prep.status == 1, o["bool_cst_x"])
+    assert np.array_equal(prep.status != 0, o["bool_rmvd_x"])
+    assert np.array_equal(np.flatnonzero(prep.status == 0), o["kept"])
+    assert np.array_equal(np.where(prep.status == 2, prep.dup_of, -1), o["dup_of"])
+    assert np.abs(ctx.get_x() - o["X"]).max() <= TOL
+    assert np.abs(ctx.get_y() - np.where(np.isnan(o["Y"]), 0.0, o["Y"])).max() <= TOL
+
+
 def check_against_host(dat_h, prep, ctx, Y_raw):
     assert prep.p == dat_h["X"].shape[1]
     assert np.array_equal(prep.status != 0, dat_h["bool_rmvd_x"])
@@ -64,6 +77,7 @@ def test_prep_doubles_matches_host(n, p, q, na):
     with_prep = device.PreparedPredictors(G)
     with with_prep.context(Y) as ctx:
         check_against_host(dat_h, with_prep, ctx, Y)
+        check_against_oracle(G, Y, with_prep, ctx)
     assert with_prep.launch_count() >= 2  # moments + duplicate verification ran on the device
     with_prep.close()
 
@@ -78,6 +92,7 @@ def test_prep_packed_genotypes_matches_host(n, p, q):
     prep = device.PreparedPredictors(packed=packed, n=n)
     with prep.context(Y) as ctx:
         check_against_host(dat_h, prep, ctx, Y)
+        check_against_oracle(G, Y, prep, ctx)
     # padded column stride
     wide = np.zeros((p, packed.shape[1] + 5), np.uint8)
     wide[:, :packed.shape[1]] = packed

@@ -154,3 +154,30 @@ def test_masked_primal_sweep_matches_reference_mis_loop(oracle_built):
     assert np.abs(beta - beta_r).max() <= 1e-12
     # the reference's running X'(mis o X) beta equals X'(mis o Y - R)
     np.testing.assert_allclose(X.T @ (mi["Y"] - R), cbx, atol=1e-9)
+
+
+def test_prepare_oracle_and_host_mirror_agree():
+    """The literal restatement of R's scale / rm_constant_ / rm_collinear_ (oracle/prepare_oracle.py) and the package's
+    vectorised host mirror (atlasqtl_b200/prepare.py) are two independent computations of prepare_data_."""
+    from atlasqtl_b200 import prepare
+    from oracle import prepare_oracle
+    rng = np.random.default_rng(8)
+    G = rng.binomial(2, 0.3, size=(80, 40)).astype(np.float64)
+    G[:, 1::9] = rng.normal(1.0, 3.0, size=(80, len(range(1, 40, 9))))
+    G[:, 4] = 1.0
+    G[:, 13] = 0.5
+    G[:, 30] = G[:, 7]
+    G[:, 31] = G[:, 7]
+    G[:, 2] = G[:, 38]
+    Y = rng.normal(size=(80, 6)) + 2.0
+    Y[rng.uniform(size=Y.shape) < 0.1] = np.nan
+    o = prepare_oracle.prepare_data_(Y, G)
+    h = prepare.prepare_data_(Y, G, 0.1, 10)
+    assert np.array_equal(o["bool_rmvd_x"], h["bool_rmvd_x"])
+    assert o["bool_cst_x"].sum() == 2 and o["bool_coll_x"].sum() == 3
+    assert list(o["dup_of"][[30, 31, 38]]) == [7, 7, 2]
+    assert h["rmvd_coll_x"] == {"Cov_x_8": ["Cov_x_31", "Cov_x_32"], "Cov_x_3": ["Cov_x_39"]}
+    np.testing.assert_allclose(o["X"], h["X"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(o["Y"], h["Y"], rtol=0, atol=1e-13, equal_nan=True)
+    n = G.shape[0]
+    np.testing.assert_allclose((o["X"] ** 2).sum(axis=0), n - 1, rtol=1e-12)   # the sweep's pre-condition
