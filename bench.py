@@ -276,6 +276,9 @@ def main():
         from atlasqtl_b200.dist import TorchComm
         # NCCL writes its debug output (the version banner at NCCL_DEBUG=VERSION / WARN) to stdout: send it to stderr so
         # that stdout carries the ONE JSON line only
+        # (NCCL honours NCCL_DEBUG_FILE only above the VERSION level)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         comm = TorchComm()
