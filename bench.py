@@ -233,6 +233,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries the ONE JSON line and nothing else: whatever libraries print there (NCCL's version banner, ...) is
+    # sent to stderr by pointing fd 1 at fd 2 for the run; the line itself goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -261,7 +270,7 @@ def main():
                 "config": config, "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "value_at_full_p_est": res["value_at_full_p_est"],
                 "e2e": {"value": res["value"], "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     import torch
@@ -372,7 +381,7 @@ def main():
             line["cpu_port"] = port_sample(X, Y, init)
         except Exception as e:  # the baseline is a report, never the product path
             line["cpu_baseline"] = {"error": repr(e)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
 
