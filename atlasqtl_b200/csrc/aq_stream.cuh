@@ -99,6 +99,15 @@ constexpr int kTabRowsPerBlock = 8;
 // Everything the table pass needs about the standard normal at one point u, from ONE erfcx, ONE exp, one log and
 // one log1p:  with a = |u|/sqrt2, E = erfcx(a), e2 = exp(-u^2/2):  Q = E e2 / 2 is the tail mass beyond |u|,
 //   log Q = log(E/2) - u^2/2,  log(1-Q) = log1p(-Q),  phi/Q = sqrt(2/pi)/E  (no exp),  phi/(1-Q) = e2/(sqrt(2 pi)(1-Q)).
+// 1 / d for d in [2^-100, 2^100]: hardware seed (20 bits) times (1 + e + e^2), relative error e^3 < 1e-18 plus one rounding.
+// The IEEE division costs ~4x as many fp64 operations, and this pass is bound by exactly those.
+__device__ __forceinline__ double fast_rcp(double d) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double e0 = fma(-d, y, 1.0);
+    return fma(y, fma(e0, e0, e0), y);
+}
+
 struct NormalPoint {
     double log_tail, log_body;  // log Q, log(1 - Q)
     double r_tail, r_body;      // phi / Q, phi / (1 - Q)
@@ -114,9 +123,9 @@ __device__ __forceinline__ NormalPoint normal_point(double u, bool want_logs, bo
         o.log_tail = log(0.5 * E) - 0.5 * u * u;
         o.log_body = log1p(-Q);
     }
-    if (want_ratios) {
-        o.r_tail = kSqrt2OverPi / E;
-        o.r_body = kInvSqrt2Pi * e2 / (1.0 - Q);
+    if (want_ratios) {   // E in [0.01, 1], 1 - Q in [0.5, 1]
+        o.r_tail = kSqrt2OverPi * fast_rcp(E);
+        o.r_body = kInvSqrt2Pi * e2 * fast_rcp(1.0 - Q);
     }
     return o;
 }
@@ -130,9 +139,9 @@ __device__ __forceinline__ double normal_point_logodds(double u, bool want_ratio
     const double E = erfcx(a);
     const double e2 = exp(-0.5 * u * u);
     const double Q = 0.5 * E * e2;
-    const double inv = 1.0 / (1.0 - Q);
+    const double inv = fast_rcp(1.0 - Q);
     if (want_ratios) {
-        r_tail = kSqrt2OverPi / E;
+        r_tail = kSqrt2OverPi * fast_rcp(E);
         r_body = kInvSqrt2Pi * e2 * inv;
     }
     return log(0.5 * E * inv) - 0.5 * u * u;
