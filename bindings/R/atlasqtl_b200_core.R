@@ -42,3 +42,8 @@ coreDualLoop <- function(cp_X, cp_Y_X, gam_vb, log_Phi_theta_plus_zeta, log_1_mi
                   log_1_min_Phi_theta_plus_zeta, log_sig2_inv_vb, log_tau_vb, m1_beta, cp_betaX_X, mu_beta_vb,
                   sig2_beta_vb, tau_vb, shuffled_ind, sample_q, c))
 }
+#
+# Pre-processing on the device (prepare_data_, R/prepare_atlasqtl.R:57-83; optional, see INTEGRATION.md section 2e):
+#   :57-72   scale(X), rm_constant_, rm_collinear_  ->  pr <- .Call(`_atlasqtl_aq_prep_x`, X, 0L)   # or _atlasqtl_aq_prep_geno
+#                                                       bool_cst_x <- pr$status == 1L; bool_rmvd_x <- pr$status != 0L
+#   :83      scale(Y, center = TRUE, scale = FALSE) ->  ctx <- .Call(`_atlasqtl_aq_create_prepared`, pr$prep, Y)  (replaces aq_create)
