@@ -31,10 +31,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the main sweep kernel, from the committed
-# `ncu --set full` capture of this very command (profiles/r1_ncu_sweep_c2_full_v6.txt, tools/profile_c2.sh): 41.39 GB +
+# `ncu --set full` capture of this very command (profiles/r1_ncu_sweep_c2_full_v7.txt, tools/profile_c2.sh): 43.77 GB +
 # 15.75 GB for 1184 of the 1250 trait tiles; the algorithmic figure is 56 B per update (read gam, mu, D, W, I0; write gam,
 # mu) = 53 GB for them, + 0.5 GB of per-tile row-sum partials.
-NCU_TRAFFIC_BYTES = {("C2", 1): 57.15e9}
+NCU_TRAFFIC_BYTES = {("C2", 1): 59.53e9}
 
 FP64_PEAK_TFLOPS = 37.05  # measured DMMA m8n8k4 peak on this pool's B200 (profiles/r1_fp64_peaks_microbench.txt);
                           # MEASURED_PEAKS.json has no fp64 entry (bf16 / HBM only)
