@@ -169,7 +169,8 @@ def test_size_independent_properties_at_scale():
     """BASELINE config C4 dimensions (n=500, p=10000, q=5000): no CPU oracle at this size, so check properties:
     (1) the residual the sweep carried equals Y - X beta rebuilt from scratch from the downloaded state;
     (2) a sweep at the fixed point of another sweep changes nothing it should not (column sums are consistent);
-    (3) gam_vb stays in [0, 1] and finite."""
+    (3) gam_vb stays in [0, 1] and finite;
+    (4) the row sums of the Z part from the sweep's per-tile partials equal those of the streaming kernel."""
     import bench
     from atlasqtl_b200.device import SweepContext
     cfg, X, Y, hyper, init = bench.make_workload("C4", 0, 5000)
@@ -181,8 +182,14 @@ def test_size_independent_properties_at_scale():
         ctx.set_state(init["gam_vb"], init["mu_beta_vb"])
         ctx.refresh_tables(init["theta_vb"], init["zeta_vb"])
         out = ctx.sweep(1.0, 0.0, tau, np.zeros(q), sig2)
+        rows_fused = ctx.rowsums_zpart()   # per-tile partials left by the sweep (+ one streamed row for the tail's traits)
+        ctx.refresh_tables(init["theta_vb"], init["zeta_vb"])   # same tables again; drops the partials
+        rows_streamed = ctx.rowsums_zpart()                     # streaming pass over gam, W, I0
         st = ctx.get_state()
         again = ctx.set_state(st["gam_vb"], st["mu_beta_vb"])  # rebuilds Y - X beta from scratch (mode 1)
+    # (4) both routes to rowSums of the Z part agree, and add up to the column-sum route
+    np.testing.assert_allclose(rows_fused, rows_streamed, rtol=1e-11, atol=1e-9)
+    assert abs(rows_fused.sum() - out["colsum_zpart"].sum()) <= 1e-10 * np.abs(out["colsum_zpart"]).sum()
     assert np.isfinite(st["gam_vb"]).all() and st["gam_vb"].min() >= 0 and st["gam_vb"].max() <= 1
     np.testing.assert_allclose(out["resid_sq"], again["resid_sq"], rtol=1e-9)
     np.testing.assert_allclose(out["colsum_gam"], st["gam_vb"].sum(axis=0), rtol=1e-11)
