@@ -162,22 +162,53 @@ def checkpoint_(it, checkpoint_path, ctx, theta_vb, zeta_vb, converged, lb_new, 
     if checkpoint_path is None or it % rate != 0:
         return None
     rank, world = (comm.rank, comm.world_size) if comm is not None else (0, 1)
-    st = ctx.get_state(gam=True, mu=extra is not None, beta=True)
-    fields = dict(beta_vb=st["beta_vb"], gam_vb=st["gam_vb"], theta_vb=theta_vb, zeta_vb=zeta_vb,
-                  converged=converged, it=it, lb_new=lb_new, diff_lb=abs(lb_new - lb_old))
+    fields = dict(theta_vb=np.array(theta_vb), zeta_vb=np.array(zeta_vb), converged=converged, it=it, lb_new=lb_new,
+                  diff_lb=abs(lb_new - lb_old))
     if lam2_inv_vb is not None:
-        fields["lam2_inv_vb"] = lam2_inv_vb
+        fields["lam2_inv_vb"] = np.array(lam2_inv_vb)
     if sig02_inv_vb is not None:
         fields["sig02_inv_vb"] = sig02_inv_vb
     if extra is not None:
-        fields["mu_beta_vb"] = st["mu_beta_vb"]
-        fields.update(extra)
+        fields.update({k: np.array(v) for k, v in extra.items()})
     path = _checkpoint_file(checkpoint_path, it, rank, world)
-    np.savez(path, **fields)
     old = _checkpoint_file(checkpoint_path, it - 2 * rate, rank, world)
-    if os.path.exists(old):
-        os.remove(old)
-    return path
+
+    def write(fetch):
+        st = fetch(gam=True, mu=extra is not None, beta=True)
+        fields.update(beta_vb=st["beta_vb"], gam_vb=st["gam_vb"])
+        if extra is not None:
+            fields["mu_beta_vb"] = st["mu_beta_vb"]
+        np.savez(path, **fields)
+        if os.path.exists(old):
+            os.remove(old)
+        return path
+
+    if hasattr(ctx, "snapshot"):
+        # device path: freeze the state in stream order (milliseconds), then transpose / download / write on a host thread
+        # and a copy stream while the sweeps go on (include/atlasqtl_b200.h, aq_snapshot / aq_snapshot_fetch)
+        checkpoint_join_(ctx)
+        ctx.snapshot()
+        ctx._ckpt_future = _checkpoint_pool().submit(write, ctx.snapshot_fetch)
+        return path
+    return write(ctx.get_state)
+
+
+_CKPT = None
+
+
+def _checkpoint_pool():
+    global _CKPT
+    if _CKPT is None:
+        _CKPT = ThreadPoolExecutor(1)
+    return _CKPT
+
+
+def checkpoint_join_(ctx):
+    """Wait for a checkpoint still being written in the background (re-raises what it raised)."""
+    fut = getattr(ctx, "_ckpt_future", None)
+    if fut is not None:
+        ctx._ckpt_future = None
+        fut.result()
 
 
 def checkpoint_clean_up_(checkpoint_path, comm=None):
@@ -486,6 +517,7 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
                         comm=comm, rate=checkpoint_rate,
                         extra=dict(tau_vb=tau_vb, sig2_beta_vb=sig2_beta_vb, sig2_theta_vb=sig2_theta_vb))  # :379-381
 
+        checkpoint_join_(ctx)
         if not keep_checkpoints:
             checkpoint_clean_up_(checkpoint_path, comm)  # :388
         if iter_hook is not None:
@@ -512,5 +544,9 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
                        cp_X_Xbeta=None)
         return out
     finally:
+        try:
+            checkpoint_join_(ctx)
+        except Exception:
+            pass
         if own_ctx:
             ctx.close()

@@ -113,6 +113,12 @@ struct aq_ctx {
     int rowpart_cap = 0, rowpart_rows = 0;   // rows allocated / rows the last sweep wrote (0: not valid)
     int rowpart_k_tail = -1;                 // first trait NOT covered by those rows (-1: all are)
     bool rowpart_tried = false;
+    // asynchronous state hand-off (aq_snapshot / aq_snapshot_fetch): device copies of gam / mu, a second staging buffer,
+    // a copy stream and the event that orders it after the snapshot
+    double *snap_gam = nullptr, *snap_mu = nullptr, *stage2 = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_snap = nullptr;
+    bool have_snap = false;
     double* sel_partial = nullptr;  // scratch of the selection kernels: 2 x kSelBlocks partials + 2 results
     std::vector<int32_t> order, order_pad;
     std::vector<double> hbuf;   // pinned-size-agnostic host scratch
@@ -415,12 +421,15 @@ int aq_destroy(aq_ctx* c) {
         if (b) cudaFree(b);
     if (c->order_dev) cudaFree(c->order_dev);
     if (c->mask) cudaFree(c->mask);
-    for (double* b : {c->xnsq, c->n_obs, c->mis_out, c->sel_partial, c->rowpart})
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    for (double* b : {c->xnsq, c->n_obs, c->mis_out, c->sel_partial, c->rowpart, c->snap_gam, c->snap_mu, c->stage2})
         if (b) cudaFree(b);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : {c->evr0, c->evr1, c->evt0, c->evt1})
         if (e) cudaEventDestroy(e);
+    if (c->ev_snap) cudaEventDestroy(c->ev_snap);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return AQ_OK;
@@ -829,6 +838,51 @@ int aq_get_state(aq_ctx* c, double* gam_vb, double* mu_beta_vb, double* beta_vb)
     if (gam_vb && (rc = download_pxq(c, c->gam, nullptr, 0, gam_vb)) != AQ_OK) return rc;
     if (mu_beta_vb && (rc = download_pxq(c, c->mu, nullptr, 0, mu_beta_vb)) != AQ_OK) return rc;
     if (beta_vb && (rc = download_pxq(c, c->gam, c->mu, 1, beta_vb)) != AQ_OK) return rc;
+    return AQ_OK;
+}
+
+int aq_snapshot(aq_ctx* c) {
+    if (!c) return fail(AQ_EINVAL, "NULL context");
+    if (!c->have_state) return fail(AQ_ESTATE, "aq_snapshot before aq_set_state");
+    AQ_CUDA(cudaSetDevice(c->device));
+    const size_t pq = (size_t)c->p_pad * c->q_pad;
+    if (!c->copy_stream) {
+        AQ_CUDA(cudaMalloc((void**)&c->snap_gam, sizeof(double) * pq));
+        AQ_CUDA(cudaMalloc((void**)&c->snap_mu, sizeof(double) * pq));
+        AQ_CUDA(cudaMalloc((void**)&c->stage2, sizeof(double) * (size_t)c->stage_cols * c->p));
+        AQ_CUDA(cudaEventCreateWithFlags(&c->ev_snap, cudaEventDisableTiming));
+        AQ_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    }
+    AQ_CUDA(cudaStreamSynchronize(c->copy_stream));   // a fetch of the previous snapshot has finished reading it
+    AQ_CUDA(cudaMemcpyAsync(c->snap_gam, c->gam, sizeof(double) * pq, cudaMemcpyDeviceToDevice, c->stream));
+    AQ_CUDA(cudaMemcpyAsync(c->snap_mu, c->mu, sizeof(double) * pq, cudaMemcpyDeviceToDevice, c->stream));
+    AQ_CUDA(cudaEventRecord(c->ev_snap, c->stream));
+    c->have_snap = true;
+    return AQ_OK;
+}
+
+int aq_snapshot_fetch(aq_ctx* c, double* gam_vb, double* mu_beta_vb, double* beta_vb) {
+    if (!c) return fail(AQ_EINVAL, "NULL context");
+    if (!c->have_snap) return fail(AQ_ESTATE, "aq_snapshot_fetch before aq_snapshot");
+    AQ_CUDA(cudaSetDevice(c->device));
+    AQ_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_snap, 0));
+    // touches the snapshot, the second staging buffer and the copy stream only: may run on another host thread while
+    // the owner of the context keeps sweeping
+    double* outs[3] = {gam_vb, mu_beta_vb, beta_vb};
+    for (int which = 0; which < 3; ++which) {
+        if (!outs[which]) continue;
+        const double* a = which == 1 ? c->snap_mu : c->snap_gam;
+        const double* b = which == 2 ? c->snap_mu : nullptr;
+        for (int k0 = 0; k0 < c->q; k0 += c->stage_cols) {
+            const int kc = std::min(c->stage_cols, c->q - k0);
+            dim3 grid((c->p + 31) / 32, (kc + 31) / 32), block(32, 8);
+            dev_to_cm_kernel<<<grid, block, 0, c->copy_stream>>>(a, b, which == 2 ? 1 : 0, c->p, kc, k0, c->q_pad, c->stage2);
+            AQ_CUDA(cudaGetLastError());
+            AQ_CUDA(cudaMemcpyAsync(outs[which] + (size_t)k0 * c->p, c->stage2, sizeof(double) * (size_t)kc * c->p,
+                                    cudaMemcpyDeviceToHost, c->copy_stream));
+            AQ_CUDA(cudaStreamSynchronize(c->copy_stream));
+        }
+    }
     return AQ_OK;
 }
 

@@ -93,6 +93,17 @@ class SweepContext:
         _lib.check(self._lib.aq_get_state(self._ctx, *[_lib.dptr(x) for x in outs]))
         return dict(gam_vb=outs[0], mu_beta_vb=outs[1], beta_vb=outs[2])
 
+    def snapshot(self):
+        """Freeze gam_vb / mu_beta_vb on the device in stream order (aq_snapshot); later sweeps do not disturb it."""
+        _lib.check(self._lib.aq_snapshot(self._ctx))
+
+    def snapshot_fetch(self, gam=True, mu=True, beta=True):
+        """Download the frozen state (aq_snapshot_fetch) on the copy stream; may run on another thread while this
+        context keeps sweeping."""
+        outs = [np.empty((self.p, self.q), order="F") if f else None for f in (gam, mu, beta)]
+        _lib.check(self._lib.aq_snapshot_fetch(self._ctx, *[_lib.dptr(x) for x in outs]))
+        return dict(gam_vb=outs[0], mu_beta_vb=outs[1], beta_vb=outs[2])
+
     def get_residual(self):
         r = np.empty((self.n, self.q), order="F")
         _lib.check(self._lib.aq_get_residual(self._ctx, _lib.dptr(r)))

@@ -116,6 +116,17 @@ int aq_set_state(aq_ctx* ctx, const double* gam_vb, const double* mu_beta_vb,
 /* Copy the state back in R layout (any pointer may be NULL): the in-place outputs of coreDualLoop. */
 int aq_get_state(aq_ctx* ctx, double* gam_vb, double* mu_beta_vb, double* beta_vb);
 
+/*
+ * Asynchronous hand-off of the state for checkpoints (checkpoint_, R/utils.R:571-627: gam_vb / beta_vb every 100
+ * iterations) and outputs.  aq_snapshot copies gam_vb and mu_beta_vb device-to-device in stream order (milliseconds),
+ * so the sweeps issued afterwards do not disturb it; aq_snapshot_fetch transposes and downloads THAT copy on a second
+ * stream (same outputs as aq_get_state, any may be NULL) and returns once the host buffers are filled.  It touches the
+ * snapshot only, so it may be called from another host thread while the context's owner keeps sweeping -- the one
+ * exception to the one-thread-at-a-time rule.  One snapshot at a time: aq_snapshot waits for a fetch in flight.
+ */
+int aq_snapshot(aq_ctx* ctx);
+int aq_snapshot_fetch(aq_ctx* ctx, double* gam_vb, double* mu_beta_vb, double* beta_vb);
+
 /* Residual Y - X beta_vb (n x q_local), mainly for tests: X'(Y - residual) is the reference's cp_betaX_X. */
 int aq_get_residual(aq_ctx* ctx, double* resid);
 
