@@ -80,6 +80,18 @@ SEXP _atlasqtl_aq_get_state(SEXP ptr, SEXP gam_vb, SEXP mu_beta_vb, SEXP beta_vb
   return R_NilValue;
 }
 
+/* Checkpoints without a stall: freeze the state on the device now (milliseconds) ... */
+SEXP _atlasqtl_aq_snapshot(SEXP ptr) {
+  check(aq_snapshot(get_ctx(ptr)));
+  return R_NilValue;
+}
+/* ... and fill the matrices later (e.g. just before saveRDS in checkpoint_): the sweeps issued in between ran on the main
+ * stream while nothing was copied; a package that owns a worker thread may call aq_snapshot_fetch from it instead */
+SEXP _atlasqtl_aq_snapshot_fetch(SEXP ptr, SEXP gam_vb, SEXP mu_beta_vb, SEXP beta_vb) {
+  check(aq_snapshot_fetch(get_ctx(ptr), dbl_or_null(gam_vb), dbl_or_null(mu_beta_vb), dbl_or_null(beta_vb)));
+  return R_NilValue;
+}
+
 SEXP _atlasqtl_aq_refresh_tables(SEXP ptr, SEXP theta_vb, SEXP zeta_vb, SEXP c_next, SEXP want_elbo) {
   double part = NA_REAL;
   check(aq_refresh_tables(get_ctx(ptr), REAL(theta_vb), REAL(zeta_vb), Rf_asReal(c_next),
@@ -221,6 +233,8 @@ static const R_CallMethodDef CallEntries[] = {
     {"_atlasqtl_aq_set_order", (DL_FUNC)&_atlasqtl_aq_set_order, 2},
     {"_atlasqtl_aq_set_state", (DL_FUNC)&_atlasqtl_aq_set_state, 3},
     {"_atlasqtl_aq_get_state", (DL_FUNC)&_atlasqtl_aq_get_state, 4},
+    {"_atlasqtl_aq_snapshot", (DL_FUNC)&_atlasqtl_aq_snapshot, 1},
+    {"_atlasqtl_aq_snapshot_fetch", (DL_FUNC)&_atlasqtl_aq_snapshot_fetch, 4},
     {"_atlasqtl_aq_refresh_tables", (DL_FUNC)&_atlasqtl_aq_refresh_tables, 5},
     {"_atlasqtl_aq_sweep", (DL_FUNC)&_atlasqtl_aq_sweep, 6},
     {"_atlasqtl_aq_rowsums_zpart", (DL_FUNC)&_atlasqtl_aq_rowsums_zpart, 2},
