@@ -846,13 +846,12 @@ int aq_snapshot(aq_ctx* c) {
     if (!c->have_state) return fail(AQ_ESTATE, "aq_snapshot before aq_set_state");
     AQ_CUDA(cudaSetDevice(c->device));
     const size_t pq = (size_t)c->p_pad * c->q_pad;
-    if (!c->copy_stream) {
-        AQ_CUDA(cudaMalloc((void**)&c->snap_gam, sizeof(double) * pq));
-        AQ_CUDA(cudaMalloc((void**)&c->snap_mu, sizeof(double) * pq));
-        AQ_CUDA(cudaMalloc((void**)&c->stage2, sizeof(double) * (size_t)c->stage_cols * c->p));
-        AQ_CUDA(cudaEventCreateWithFlags(&c->ev_snap, cudaEventDisableTiming));
-        AQ_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    }
+    // (each resource on its own: a call that failed half-way leaves nothing to leak or to allocate twice)
+    if (!c->snap_gam) AQ_CUDA(cudaMalloc((void**)&c->snap_gam, sizeof(double) * pq));
+    if (!c->snap_mu) AQ_CUDA(cudaMalloc((void**)&c->snap_mu, sizeof(double) * pq));
+    if (!c->stage2) AQ_CUDA(cudaMalloc((void**)&c->stage2, sizeof(double) * (size_t)c->stage_cols * c->p));
+    if (!c->ev_snap) AQ_CUDA(cudaEventCreateWithFlags(&c->ev_snap, cudaEventDisableTiming));
+    if (!c->copy_stream) AQ_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     AQ_CUDA(cudaStreamSynchronize(c->copy_stream));   // a fetch of the previous snapshot has finished reading it
     AQ_CUDA(cudaMemcpyAsync(c->snap_gam, c->gam, sizeof(double) * pq, cudaMemcpyDeviceToDevice, c->stream));
     AQ_CUDA(cudaMemcpyAsync(c->snap_mu, c->mu, sizeof(double) * pq, cudaMemcpyDeviceToDevice, c->stream));
@@ -1040,12 +1039,10 @@ int aq_set_missing(aq_ctx* c, const double* mis_pat, double* n_obs) {
     if (c->n > 2048) return fail(AQ_EUNSUPPORTED, "aq_set_missing: the missing-response kernel covers n <= 2048");
     AQ_CUDA(cudaSetDevice(c->device));
     const size_t pq = (size_t)c->p_pad * c->q_pad;
-    if (!c->mask) {
-        AQ_CUDA(cudaMalloc((void**)&c->mask, sizeof(unsigned long long) * 32 * (size_t)c->q_pad));
-        AQ_CUDA(cudaMalloc((void**)&c->xnsq, sizeof(double) * pq));
-        AQ_CUDA(cudaMalloc((void**)&c->n_obs, sizeof(double) * c->q_pad));
-        AQ_CUDA(cudaMalloc((void**)&c->mis_out, sizeof(double) * kMisOutputs * (size_t)c->q_pad));
-    }
+    if (!c->mask) AQ_CUDA(cudaMalloc((void**)&c->mask, sizeof(unsigned long long) * 32 * (size_t)c->q_pad));
+    if (!c->xnsq) AQ_CUDA(cudaMalloc((void**)&c->xnsq, sizeof(double) * pq));
+    if (!c->n_obs) AQ_CUDA(cudaMalloc((void**)&c->n_obs, sizeof(double) * c->q_pad));
+    if (!c->mis_out) AQ_CUDA(cudaMalloc((void**)&c->mis_out, sizeof(double) * kMisOutputs * (size_t)c->q_pad));
     AQ_CUDA(cudaMemsetAsync(c->xnsq, 0, sizeof(double) * pq, c->stream));
     AQ_CUDA(cudaMemsetAsync(c->mask, 0, sizeof(unsigned long long) * 32 * (size_t)c->q_pad, c->stream));
     // the n x q pattern goes through the residual buffer (same [q][ld] orientation, ld >= n), which is rebuilt by set_state
