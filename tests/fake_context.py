@@ -115,3 +115,19 @@ class OracleSweepContext:
 
     def last_sweep_ms(self):
         return float("nan")
+
+
+class SnapshotOracleSweepContext(OracleSweepContext):
+    """The test double with the asynchronous hand-off of the real context (aq_snapshot / aq_snapshot_fetch): the host
+    loop then writes its checkpoints on a worker thread."""
+
+    def snapshot(self):
+        self._snap = (self.gam.copy(), self.mu.copy())
+        self.snapshots = getattr(self, "snapshots", 0) + 1
+
+    def snapshot_fetch(self, gam=True, mu=True, beta=True):
+        import threading
+        self.fetch_threads = getattr(self, "fetch_threads", set()) | {threading.current_thread().name}
+        g, m = self._snap
+        return dict(gam_vb=g.copy() if gam else None, mu_beta_vb=m.copy() if mu else None,
+                    beta_vb=(g * m) if beta else None)

@@ -52,19 +52,29 @@ def test_rejects_what_this_build_does_not_cover():
         core.atlasqtl_global_local_core_(Y, X, 5, None, 1, 0.1, 5, 0, hyper, init, trace_path="/tmp/x")
 
 
-def test_checkpoints_and_resume(oracle_built, tmp_path):
+@pytest.mark.parametrize("background", [False, True])
+def test_checkpoints_and_resume(oracle_built, tmp_path, background):
     """checkpoint_ / checkpoint_clean_up_ (R/utils.R:571-627): files every `rate` iterations with the reference's fields,
     only the last two kept, removed at the end; and (extension) a run restarted from a checkpoint lands on the same
-    optimum."""
+    optimum.  background: the context offers snapshot / snapshot_fetch, so the files are written on a worker thread."""
     import glob
+    from fake_context import SnapshotOracleSweepContext
     X, Y, hyper, init = make_problem(100, 75, 20, p_act=10, q_act=20, maf=0.2, p0=(5, 25))
     q = Y.shape[1]
     base = str(tmp_path) + "/"
-    fac = lambda X_, Y_: OracleSweepContext(X_, Y_)
+    made = []
+
+    def fac(X_, Y_):
+        made.append((SnapshotOracleSweepContext if background else OracleSweepContext)(X_, Y_))
+        return made[-1]
     ref = core.atlasqtl_global_local_core_(Y, X, q, None, 1, 0.1, 1000, 0, hyper, init, context_factory=fac)
     out = core.atlasqtl_global_local_core_(Y, X, q, None, 1, 0.1, 1000, 0, hyper, init, checkpoint_path=base,
                                            checkpoint_rate=10, keep_checkpoints=True, context_factory=fac)
     assert np.array_equal(out["gam_vb"], ref["gam_vb"])            # checkpointing does not perturb the run
+    if background:
+        ctx = made[1]
+        assert ctx.snapshots == out["it"] // 10 and ctx._ckpt_future is None     # every writer has been joined
+        assert all(not name.startswith("MainThread") for name in ctx.fetch_threads)
     files = sorted(glob.glob(base + "tmp_output_it_*.npz"), key=lambda f: int(f.split("_it_")[1][:-4]))
     its = [int(f.split("_it_")[1][:-4]) for f in files]
     assert its == [i for i in range(10, out["it"] + 1, 10)][-2:]   # only the last two are kept
