@@ -51,6 +51,8 @@ def atlasqtl(Y, X, p0, anneal=(1, 2, 10), tol=0.1, maxit=1000, user_seed=None, v
                                            list_init, checkpoint_path, trace_path, full_output, thinned_elbo_eval,
                                            debug=True, comm=comm, slab=slab, device=device, order_fn=order_fn,
                                            trace=trace, context_factory=context_factory)
+    if hasattr(Xp, "close"):
+        Xp.close()  # device path: the raw predictors held for aq_create_prepared are no longer needed
     if comm is not None and comm.world_size > 1:
         res = comm.gather_result(res, q)
     res["p0"] = p0
