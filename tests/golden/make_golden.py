@@ -52,8 +52,44 @@ def run_reference(d):
     return dict(log_Phi=lp, log_1_min_Phi=lq, out_gam=gam, out_mu=mu, out_beta=beta, out_cp_betaX_X=cbx)
 
 
+def run_reference_mis(d, frac=0.1, seed=17):
+    """The reference's coreDualMisLoop (src/coreLoop.cpp:91-138) with the set-up of R/atlasqtl_global_local_core.R:19-33:
+    mis_pat, Y zeroed where missing, X_norm_sq, the list cp_X_rm of per-trait Gram corrections, p x q sig2_beta_vb."""
+    X, Y = d["X"], d["Y"]
+    n, p = X.shape
+    q = Y.shape[1]
+    rng = np.random.default_rng(seed)
+    mis = (rng.uniform(size=(n, q)) >= frac).astype(np.float64)
+    mis[:, ::3] = 1.0
+    mis = np.asfortranarray(mis)
+    Ym = np.asfortranarray(Y * mis)
+    xnsq = np.asfortranarray((X ** 2).T @ mis)
+    sig2_inv = 0.8
+    sig2_beta = np.asfortranarray(1.0 / (d["c"] * (xnsq + sig2_inv) * d["tau"][None, :]))
+    u = d["theta"][:, None] + d["zeta"][None, :]
+    lp, lq = np.asfortranarray(sp.log_ndtr(u)), np.asfortranarray(sp.log_ndtr(-u))
+    cp_X = np.asfortranarray(X.T @ X)
+    cp_X_rm = np.zeros((p, p, q), order="F")
+    for k in range(q):
+        rows = np.flatnonzero(mis[:, k] == 0)
+        cp_X_rm[:, :, k] = X[rows].T @ X[rows]
+    cp_Y_X = np.asfortranarray(Ym.T @ X)
+    gam, mu = d["gam"].copy(order="F"), d["mu"].copy(order="F")
+    beta = np.asfortranarray(gam * mu)
+    cbx = np.asfortranarray(cp_X @ beta - np.stack([cp_X_rm[:, :, k] @ beta[:, k] for k in range(q)], axis=1))
+    native.ref_core_dual_mis_loop(cp_X, cp_X_rm, cp_Y_X, gam, lp, lq, d["log_sig2_inv"], d["log_tau"], beta, cbx, mu,
+                                  sig2_beta, d["tau"], d["order"], np.arange(q, dtype=np.int32), c=d["c"])
+    return dict(mis=mis, Y_mis=Ym, xnsq=xnsq, sig2_inv=sig2_inv, sig2_beta_pq=sig2_beta, log_Phi=lp, log_1_min_Phi=lq,
+                out_gam=gam, out_mu=mu, out_beta=beta, out_cp_betaX_X=cbx)
+
+
 if __name__ == "__main__":
     native.build()
+    for name, spec in (("a_shuffled_c07", (80, 57, 9, 0.7, True, 2)), ("b_identity_c1", (70, 33, 11, 1.0, False, 5))):
+        d = inputs(*spec)
+        d.update(run_reference_mis(d))
+        np.savez_compressed(os.path.join(HERE, f"coredualmisloop_{name}.npz"), **d)
+        print("mis", name, {k: getattr(v, "shape", v) for k, v in d.items() if k.startswith("out_")})
     for name, spec in CASES.items():
         d = inputs(*spec)
         d.update(run_reference(d))
