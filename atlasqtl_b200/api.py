@@ -19,9 +19,10 @@ def atlasqtl(Y, X, p0, anneal=(1, 2, 10), tol=0.1, maxit=1000, user_seed=None, v
         raise ValueError("The verbose argument must be set to 0, 1 or 2.")
     core.check_annealing_(anneal)
     if prepare_on_device or packed_n is not None:
-        dat = prepare.prepare_data_device_(Y, X, tol, maxit, user_seed, verbose, packed_n=packed_n, device=device)
+        dat = prepare.prepare_data_device_(Y, X, tol, maxit, user_seed, verbose, checkpoint_path, packed_n=packed_n,
+                                           device=device)
     else:
-        dat = prepare.prepare_data_(Y, X, tol, maxit, user_seed, verbose)
+        dat = prepare.prepare_data_(Y, X, tol, maxit, user_seed, verbose, checkpoint_path)
     Xp, Yp = dat["X"], dat["Y"]  # device path: Xp is a handle with .shape, Yp the raw responses (hyper / init use variances only)
     n, p = Xp.shape
     q = Yp.shape[1]
@@ -34,6 +35,11 @@ def atlasqtl(Y, X, p0, anneal=(1, 2, 10), tol=0.1, maxit=1000, user_seed=None, v
     elif list_hyper["p_hyper"] != p or list_hyper["q_hyper"] != q:
         raise ValueError("The dimensions of list_hyper do not match those of the (pre-processed) data.")
     if list_init is None:
+        if comm is not None and comm.world_size > 1 and user_seed is None:
+            # theta_vb, sig2_theta_vb, sig02_inv_vb are REPLICATED state: every rank must draw the same initial values, so
+            # the seed of an unseeded run is drawn once, on rank 0, and shared (all-reduce of [seed, 0, 0, ...])
+            seed0 = float(np.random.SeedSequence().entropy % (1 << 52)) if comm.rank == 0 else 0.0
+            user_seed = int(comm.allreduce_sum(np.array([seed0]))[0])
         list_init = hyper_init.auto_set_init_(Yp, p, p0, shr_fac_inv, user_seed)
     elif list_init["p_init"] != p or list_init["q_init"] != q:
         raise ValueError("The dimensions of list_init do not match those of the (pre-processed) data.")

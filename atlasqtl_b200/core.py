@@ -225,8 +225,16 @@ def checkpoint_clean_up_(checkpoint_path, comm=None):
 def init_from_checkpoint(path, list_init):
     """Extension (the reference cannot resume): a list_init that restarts the run from a checkpoint written with the
     resume fields.  theta_vb, zeta_vb, gam_vb, mu_beta_vb, tau_vb, sig2_beta_vb, sig2_theta_vb, sig02_inv_vb are taken
-    from the file, everything else from `list_init`."""
+    from the file, everything else from `list_init`.
+
+    Checkpoints are written after annealing only (like the reference's), so the restart must run with `anneal=None`:
+    the iteration counter starts again at 1 and the ELBO-thinning schedule with it, i.e. the restart continues the
+    same fixed-point iteration but is not a bit-for-bit replay of the original run's bookkeeping.  Runs with missing
+    responses are refused: their checkpoint holds the q-vector part of sig2_beta_vb only, while the state the first
+    restarted iteration needs (m2_beta with the p x q sig2_beta_vb of the saved sweep) cannot be rebuilt from it."""
     d = np.load(path)
+    if "has_missing" in d.files and bool(d["has_missing"]):
+        raise ValueError("resuming from a checkpoint of a run with missing responses is not supported")
     out = dict(list_init)
     for key in ("gam_vb", "mu_beta_vb", "theta_vb", "zeta_vb", "tau_vb", "sig2_beta_vb", "sig2_theta_vb"):
         out[key] = np.array(d[key])
@@ -513,9 +521,11 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
                 rec["c"] = c_prev
                 rec["host_ms"] = seg
                 trace.append(rec)
-            checkpoint_(it, checkpoint_path, ctx, theta_vb, zeta_vb, converged, lb_new, lb_old, lam2_inv_vb, sig02_inv_vb,
-                        comm=comm, rate=checkpoint_rate,
-                        extra=dict(tau_vb=tau_vb, sig2_beta_vb=sig2_beta_vb, sig2_theta_vb=sig2_theta_vb))  # :379-381
+            if not rec["annealing"]:  # the reference checkpoints in the non-annealed branch only (:338, :379-381)
+                checkpoint_(it, checkpoint_path, ctx, theta_vb, zeta_vb, converged, lb_new, lb_old, lam2_inv_vb,
+                            sig02_inv_vb, comm=comm, rate=checkpoint_rate,
+                            extra=dict(tau_vb=tau_vb, sig2_beta_vb=sig2_beta_vb, sig2_theta_vb=sig2_theta_vb,
+                                       has_missing=mis_pat is not None))
 
         checkpoint_join_(ctx)
         if not keep_checkpoints:

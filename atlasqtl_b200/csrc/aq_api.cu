@@ -108,11 +108,17 @@ struct aq_ctx {
     // missing responses (aq_set_missing): bit masks, X_norm_sq, per-trait observation counts and the sums of the NA kernels
     unsigned long long* mask = nullptr;
     double *xnsq = nullptr, *n_obs = nullptr, *mis_out = nullptr;
+    double* sig2tab = nullptr;  // explicit p x q sig2_beta_vb (stateless coreDualMisLoop entry only)
     bool has_mis = false;
     double* rowpart = nullptr;      // [rowpart_cap][p_pad] per-tile row sums of gam W + I0 left by the last aq_sweep
     int rowpart_cap = 0, rowpart_rows = 0;   // rows allocated / rows the last sweep wrote (0: not valid)
     int rowpart_k_tail = -1;                 // first trait NOT covered by those rows (-1: all are)
     bool rowpart_tried = false;
+    // launch attributes of the context's two kernel configurations (0: main, 1: 8-trait tail variant), set on first use
+    bool attr_done[2] = {false, false};
+    int max_groups[2] = {0, 0};       // tiles one round of the persistent grid processes (SMs, or schedulable clusters)
+    int* seg_done = nullptr;          // segmented sweeps: per-tile hand-off counters
+    int last_nseg = 1;                // SNP segments per tile of the last sweep launch
     // asynchronous state hand-off (aq_snapshot / aq_snapshot_fetch): device copies of gam / mu, a second staging buffer,
     // a copy stream and the event that orders it after the snapshot
     double *snap_gam = nullptr, *snap_mu = nullptr, *stage2 = nullptr;
@@ -146,77 +152,156 @@ struct aq_prep {
 
 namespace {
 
-// One launch of configuration C over `ntiles` trait tiles starting at trait k_base.  *groups (if not NULL) receives
-// the number of tiles one round of the persistent grid processes (SMs, or schedulable clusters).
+// Launch attributes of one kernel configuration on this context's device: set once per context (not in function statics:
+// the cluster size is a run-time value of the same template instance, and contexts live on several devices / threads).
 template <class C>
-int launch_sweep_t(aq_ctx* c, SweepParams P, int ntiles, int k_base, int* groups) {
-    static bool attr_done[64] = {false};
-    static int max_groups[64] = {0};
+int prepare_sweep_t(aq_ctx* c, int slot) {
+    if (c->attr_done[slot]) return AQ_OK;
+    const int ncta = c->cfg.ncta;
+    AQ_CUDA(cudaFuncSetAttribute(sweep_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
+    c->max_groups[slot] = c->sm_count;
+    if (C::kCl) {
+        cudaLaunchConfig_t lc{};
+        lc.blockDim = dim3(C::kThreads);
+        lc.dynamicSmemBytes = C::kSmemBytes;
+        lc.stream = c->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = ncta;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        lc.attrs = attr;
+        lc.numAttrs = 1;
+        lc.gridDim = dim3(c->sm_count / ncta * ncta);
+        int nc = 0;
+        AQ_CUDA(cudaOccupancyMaxActiveClusters(&nc, sweep_kernel<C>, &lc));
+        if (nc < 1) return fail(AQ_EUNSUPPORTED, "no thread-block cluster of the required size can be scheduled");
+        c->max_groups[slot] = nc;
+    } else {
+        int per_sm = 0;
+        AQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_kernel<C>, C::kThreads, C::kSmemBytes));
+        if (per_sm < 1) return fail(AQ_EUNSUPPORTED, "the sweep kernel does not fit on this device");
+    }
+    c->attr_done[slot] = true;
+    return AQ_OK;
+}
+
+// One launch of configuration C (slot 0: the context's main configuration, 1: its 8-trait tail variant) over `ntiles`
+// trait tiles starting at trait k_base, each cut into P.nseg SNP segments.
+template <class C>
+int launch_sweep_t(aq_ctx* c, int slot, SweepParams P, int ntiles, int k_base) {
+    int rc = prepare_sweep_t<C>(c, slot);
+    if (rc != AQ_OK) return rc;
+    if (ntiles <= 0) return AQ_OK;
     const int ncta = c->cfg.ncta;
     cudaLaunchConfig_t lc{};
     lc.blockDim = dim3(C::kThreads);
     lc.dynamicSmemBytes = C::kSmemBytes;
     lc.stream = c->stream;
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = ncta;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
     lc.attrs = attr;
-    lc.numAttrs = C::kCl ? 1 : 0;
-    if (!attr_done[c->device]) {
-        AQ_CUDA(cudaFuncSetAttribute(sweep_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
-        max_groups[c->device] = c->sm_count;
-        if (C::kCl) {
-            lc.gridDim = dim3(c->sm_count / ncta * ncta);
-            int nc = 0;
-            AQ_CUDA(cudaOccupancyMaxActiveClusters(&nc, sweep_kernel<C>, &lc));
-            if (nc < 1) return fail(AQ_EUNSUPPORTED, "no thread-block cluster of the required size can be scheduled");
-            max_groups[c->device] = nc;
-        }
-        attr_done[c->device] = true;
+    lc.numAttrs = 0;
+    if (C::kCl) {
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = ncta;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        lc.numAttrs = 1;
+    } else if (P.nseg > 1) {
+        // CTAs hand trait tiles over to one another inside the launch: all of them must be resident at the same time
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        lc.numAttrs = 1;
     }
-    if (groups) *groups = max_groups[c->device];
-    if (ntiles <= 0) return AQ_OK;
     P.ntiles = ntiles;
     P.k_base = k_base;
-    lc.gridDim = dim3(std::min(ntiles, max_groups[c->device]) * ncta);
+    const long nunits = (long)ntiles * P.nseg;
+    lc.gridDim = dim3((unsigned)std::min<long>(nunits, c->max_groups[slot]) * ncta);
     AQ_CUDA(cudaLaunchKernelEx(&lc, sweep_kernel<C>, P));
     AQ_CUDA(cudaGetLastError());
     c->launches++;
     return AQ_OK;
 }
 
-// The sweep over all trait tiles.  A persistent grid processes G tiles per round; a last, partly filled round would
-// cost as much as a full one, so when the leftover traits fit into one round of 8-trait tiles they are swept by the
-// MT = 1 variant of the same configuration instead (same X tiles and residual layout; an 8-trait tile is bound by the
-// serial chain and takes about half the time of a full tile).
+// How the trait tiles are spread over the persistent grid.  A grid of G CTAs (clusters) processes G tiles per round and
+// a partly filled last round costs as much as a full one.  Two remedies, whichever the block-count model below prefers:
+//  (a) segmented sweep (single-CTA configurations): the SNP blocks of every tile are cut into S segments and the
+//      (segment, tile) units dealt round-robin, so the last round costs 1 / S of a round; a unit costs its blocks plus
+//      ~kSegOverheadBlocks (pipeline fill / drain, residual reload);
+//  (b) leftover traits that fit into one round of 8-trait tiles are swept by the MT = 1 variant of the configuration
+//      (an 8-trait tile is bound by the serial chain and takes ~0.68 of a full tile).
+struct SweepPlan {
+    int nseg = 1, seg_len = 0;
+    int n_main = 0, n_tail = 0, k_tail = 0;
+};
+constexpr double kSegOverheadBlocks = 4.0, kTailTileCost = 0.68;
+
+SweepPlan plan_sweep(const aq_ctx* c, int G, int kT, bool clustered, bool has_tail_variant) {
+    SweepPlan pl;
+    const int ntiles = c->ntiles, nb = c->nb;
+    pl.n_main = ntiles;
+    pl.seg_len = nb;
+    const int rem = ntiles % G;
+    double best = (double)((ntiles + G - 1) / G) * (nb + kSegOverheadBlocks);
+    if (has_tail_variant && rem != 0 && !std::getenv("AQ_NO_TAIL")) {
+        const int k_tail = (ntiles - rem) * kT;
+        const int tail_tiles = (c->q - k_tail + 7) / 8;
+        if (tail_tiles <= G) {
+            const double cost = (ntiles / G + kTailTileCost) * (nb + kSegOverheadBlocks);
+            if (cost < best) {
+                best = cost;
+                pl.n_main = ntiles - rem;
+                pl.n_tail = tail_tiles;
+                pl.k_tail = k_tail;
+            }
+        }
+    }
+    if (!clustered && ntiles > G && !std::getenv("AQ_NO_SEG")) {
+        const char* force = std::getenv("AQ_NSEG");
+        for (int S = 2; S <= 64 && nb / S >= 16; ++S) {
+            if (force && S != std::atoi(force)) continue;
+            const int len = (nb + S - 1) / S;
+            const int S2 = (nb + len - 1) / len;   // segments actually needed at this length
+            const long slots = std::max<long>(S2, ((long)ntiles * S2 + G - 1) / G);
+            const double cost = (double)slots * (len + kSegOverheadBlocks);
+            if (cost < best * 0.995 || (force && S == std::atoi(force))) {
+                best = cost;
+                pl = SweepPlan{};
+                pl.nseg = S2;
+                pl.seg_len = len;
+                pl.n_main = ntiles;
+            }
+        }
+    }
+    return pl;
+}
+
 template <int NT, bool CL>
 int launch_sweep_cfg(aq_ctx* c, const SweepParams& P) {
     using Main = CfgOf<NT, CL>;
     using Tail = SweepCfg<1, NT, CL>;
-    int G = 0;
-    int rc = launch_sweep_t<Main>(c, P, 0, 0, &G);  // attributes + round size only
+    int rc = prepare_sweep_t<Main>(c, 0);
     if (rc != AQ_OK) return rc;
+    const int G = c->max_groups[0];
     const int ntiles = c->ntiles;
-    int n_main = ntiles, n_tail = 0, k_tail = 0;
-    const int rem = ntiles % G;
-    if (Main::MT > 1 && rem != 0 && !std::getenv("AQ_NO_TAIL")) {
-        k_tail = (ntiles - rem) * Main::kT;
-        const int tail_tiles = (c->q - k_tail + 7) / 8;
-        if (tail_tiles <= G) {
-            n_main = ntiles - rem;
-            n_tail = tail_tiles;
-        }
-    }
+    const SweepPlan pl = plan_sweep(c, G, Main::kT, CL, Main::MT > 1);
     SweepParams Pm = P, Pt = P;
+    Pm.nseg = pl.nseg;
+    Pm.seg_len = pl.seg_len;
+    Pt.seg_len = c->nb;
+    if (pl.nseg > 1) {
+        if (!c->seg_done) AQ_CUDA(cudaMalloc((void**)&c->seg_done, sizeof(int) * (size_t)ntiles));
+        AQ_CUDA(cudaMemsetAsync(c->seg_done, 0, sizeof(int) * (size_t)ntiles, c->stream));
+        Pm.seg_done = c->seg_done;
+    }
+    c->last_nseg = pl.nseg;
     c->rowpart_rows = 0;
     if (P.mode == 0 && !CL) {
         // per-tile row sums of gam W + I0 ride along with the sweep (aq_rowsums_zpart reduces them); without the scratch
         // buffer the streaming row-sum kernel is used instead
         if (!c->rowpart && !c->rowpart_tried) {
             c->rowpart_tried = true;
-            c->rowpart_cap = ntiles + G;
+            c->rowpart_cap = ntiles + 1;
             if (cudaMalloc((void**)&c->rowpart, sizeof(double) * (size_t)c->rowpart_cap * c->p_pad) != cudaSuccess) {
                 cudaGetLastError();
                 c->rowpart = nullptr;
@@ -225,16 +310,16 @@ int launch_sweep_cfg(aq_ctx* c, const SweepParams& P) {
         // (measured: +0.5-1 % on a tensor-bound tile, +2.5 % on the chain-bound 8-trait tail tiles and cluster tiles, whose
         // helper warp sits closer to the serial path; the streaming pass costs 24 B per update, i.e. 2-6 % of a sweep for
         // n <= 1008 and < 1 % beyond.  So: full-size single-CTA tiles only; the tail's traits get one streamed extra row.)
-        if (c->rowpart && n_main > 0 && n_main + 1 <= c->rowpart_cap && !std::getenv("AQ_NO_ROWPART")) {
+        if (c->rowpart && pl.n_main > 0 && pl.n_main + 1 <= c->rowpart_cap && !std::getenv("AQ_NO_ROWPART")) {
             Pm.rowpart = c->rowpart;
             Pm.rowpart_base = 0;
-            c->rowpart_rows = n_main;
-            c->rowpart_k_tail = n_tail > 0 ? k_tail : -1;
+            c->rowpart_rows = pl.n_main;
+            c->rowpart_k_tail = pl.n_tail > 0 ? pl.k_tail : -1;
         }
     }
     AQ_CUDA(cudaEventRecord(c->ev0, c->stream));
-    rc = launch_sweep_t<Main>(c, Pm, n_main, 0, nullptr);
-    if (rc == AQ_OK && n_tail > 0) rc = launch_sweep_t<Tail>(c, Pt, n_tail, k_tail, nullptr);
+    rc = launch_sweep_t<Main>(c, 0, Pm, pl.n_main, 0);
+    if (rc == AQ_OK && pl.n_tail > 0) rc = launch_sweep_t<Tail>(c, 1, Pt, pl.n_tail, pl.k_tail);
     if (rc != AQ_OK) {
         c->rowpart_rows = 0;
         return rc;
@@ -284,6 +369,9 @@ int launch_sweep(aq_ctx* c, int mode, double cc, double log_sig2_inv) {
     P.rowpart_base = 0;
     P.p_pad = c->p_pad;
     P.mode = mode;
+    P.nseg = 1;
+    P.seg_len = c->nb;
+    P.seg_done = nullptr;
     P.timing = nullptr;
 #ifdef AQ_TIMING
     {
@@ -387,6 +475,17 @@ int internal_load_dtab(aq_ctx* c, const double* d_host) {
     return AQ_OK;
 }
 
+int internal_load_sig2(aq_ctx* c, const double* s2_host) {
+    if (!c || !s2_host) return fail(AQ_EINVAL, "internal_load_sig2: NULL argument");
+    AQ_CUDA(cudaSetDevice(c->device));
+    if (!c->sig2tab) AQ_CUDA(cudaMalloc((void**)&c->sig2tab, sizeof(double) * (size_t)c->p_pad * c->q_pad));
+    AQ_CUDA(cudaMemsetAsync(c->sig2tab, 0, sizeof(double) * (size_t)c->p_pad * c->q_pad, c->stream));
+    int rc = upload_pxq(c, s2_host, c->sig2tab);
+    if (rc != AQ_OK) return rc;
+    AQ_CUDA(cudaStreamSynchronize(c->stream));
+    return AQ_OK;
+}
+
 int internal_fail(int code, const char* msg) { return fail(code, msg); }
 
 }  // namespace aq
@@ -420,9 +519,10 @@ int aq_destroy(aq_ctx* c) {
     for (double* b : bufs)
         if (b) cudaFree(b);
     if (c->order_dev) cudaFree(c->order_dev);
+    if (c->seg_done) cudaFree(c->seg_done);
     if (c->mask) cudaFree(c->mask);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
-    for (double* b : {c->xnsq, c->n_obs, c->mis_out, c->sel_partial, c->rowpart, c->snap_gam, c->snap_mu, c->stage2})
+    for (double* b : {c->sig2tab, c->xnsq, c->n_obs, c->mis_out, c->sel_partial, c->rowpart, c->snap_gam, c->snap_mu, c->stage2})
         if (b) cudaFree(b);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -775,6 +875,14 @@ int aq_prep_result(const aq_prep* P, uint8_t* status, int32_t* dup_of, double* m
     return AQ_OK;
 }
 
+int aq_prep_dims(const aq_prep* P, int* n, int* p_raw, int* p_kept) {
+    if (!P) return fail(AQ_EINVAL, "aq_prep_dims: NULL argument");
+    if (n) *n = P->n;
+    if (p_raw) *p_raw = P->p_raw;
+    if (p_kept) *p_kept = P->p_kept;
+    return AQ_OK;
+}
+
 int64_t aq_prep_launch_count(const aq_prep* P) { return P ? P->launches : 0; }
 
 int aq_dims(const aq_ctx* c, int* n, int* p, int* q_local, int* p_pad, int* q_pad) {
@@ -1001,6 +1109,7 @@ int launch_mis(aq_ctx* c, int mode, double cc, double log_sig2_inv, double sig2_
     P.wtab = c->wtab;
     P.i0tab = c->i0tab;
     P.xnsq = c->xnsq;
+    P.sig2tab = c->sig2tab;
     P.tau = c->tvec;
     P.log_tau = c->tvec + c->q_pad;
     P.c = cc;
@@ -1184,6 +1293,45 @@ int aq_ppi_collect(aq_ctx* c, int mode, double lo, double hi, int64_t capacity, 
 }
 
 int64_t aq_launch_count(const aq_ctx* c) { return c ? c->launches : 0; }
+
+int aq_sweep_plan(const aq_ctx* c, int* traits_per_tile, int* ntiles, int* groups, int* nseg) {
+    if (!c) return fail(AQ_EINVAL, "NULL context");
+    if (traits_per_tile) *traits_per_tile = c->cfg.kT;
+    if (ntiles) *ntiles = c->ntiles;
+    if (groups) *groups = c->max_groups[0];
+    if (nseg) *nseg = c->last_nseg;
+    return AQ_OK;
+}
+
+namespace {
+__global__ void test_logistic_kernel(const double* __restrict__ x, double* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = aq::logistic_neg(x[i]);
+}
+}  // namespace
+
+int aq_test_logistic(int device, const double* x, double* out, int n) {
+    if (!x || !out || n < 0) return fail(AQ_EINVAL, "aq_test_logistic: bad argument");
+    if (n == 0) return AQ_OK;
+    int rc = aq_device_info(device, nullptr, nullptr, nullptr);
+    if (rc != AQ_OK) return rc;
+    double *dx = nullptr, *dout = nullptr;
+    AQ_CUDA(cudaMalloc((void**)&dx, sizeof(double) * (size_t)n));
+    cudaError_t e = cudaMalloc((void**)&dout, sizeof(double) * (size_t)n);
+    if (e == cudaSuccess) e = cudaMemcpy(dx, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        test_logistic_kernel<<<(n + 255) / 256, 256>>>(dx, dout, n);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost);
+    cudaFree(dx);
+    if (dout) cudaFree(dout);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(AQ_ECUDA, std::string("aq_test_logistic: ") + cudaGetErrorString(e));
+    }
+    return AQ_OK;
+}
 
 int aq_last_sweep_ms(const aq_ctx* c, float* ms) {
     if (!c || !ms) return fail(AQ_EINVAL, "NULL argument");

@@ -49,8 +49,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Spin limit of every wait in the kernels: a protocol slip (a missed arrive, a wrong parity) traps -- the launch fails
+// with an error the host reports -- instead of hanging the GPU.  A failed try_wait suspends the warp for a while, so
+// 2^28 of them are seconds; no wait of a correct run is longer than a few blocks of work (microseconds).
+constexpr uint32_t kSpinLimit = 1u << 28;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if (++spins == kSpinLimit) __trap();
     }
 }
 // 1-D bulk copy global -> shared through the TMA engine; completion is signalled on `bar` (SASS: UBLKCP).
@@ -103,7 +109,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t raddr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {  // acquire at cluster scope
-    uint32_t ok = 0;
+    uint32_t ok = 0, spins = 0;
     while (!ok) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -112,10 +118,21 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
             : "=r"(ok)
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
+        if (!ok && ++spins == kSpinLimit) __trap();
     }
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------- inter-CTA hand-off of a trait tile (segmented sweeps)
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // ---------------------------------------------------------------- fp64 tensor-core MMA (SASS: DMMA.8x8x4)

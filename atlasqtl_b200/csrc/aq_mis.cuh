@@ -28,6 +28,7 @@ struct MisParams {
     const double* wtab;
     const double* i0tab;
     double* xnsq;           // [p_pad][q_pad]  X_norm_sq = crossprod(X^2, mis_pat)  (R/atlasqtl_global_local_core.R:23)
+    const double* sig2tab;  // [p_pad][q_pad]  explicit sig2_beta_vb (stateless entry) or NULL: formed from xnsq on the fly
     const double* tau;      // [q_pad]
     const double* log_tau;
     double c, log_sig2_inv, sig2_inv;
@@ -87,8 +88,13 @@ __global__ void __launch_bounds__(128, (M <= 16) ? 4 : 2) mis_sweep_kernel(const
             if (P.mode == 0) {
                 ww = P.wtab[off];
                 ii = P.i0tab[off];
-                a = 1.0 / (xn + P.sig2_inv);          // c sig2_beta tau: mu = a s                        (:125)
-                s2 = a / (P.c * tauk);                // sig2_beta_vb(j,k), update_sig2_beta_vb_ R/update_vb.R:47
+                if (P.sig2tab) {                      // sig2_beta_vb(j,k) handed over by the caller (src/coreLoop.cpp:102)
+                    s2 = P.sig2tab[off];
+                    a = P.c * s2 * tauk;
+                } else {
+                    a = 1.0 / (xn + P.sig2_inv);      // c sig2_beta tau: mu = a s                        (:125)
+                    s2 = a / (P.c * tauk);            // sig2_beta_vb(j,k), update_sig2_beta_vb_ R/update_vb.R:47
+                }
                 ap = P.c * (P.dtab[off] - log(s2) / 2 + cst);   // :127-129 without the mu^2 term
                 bq = P.c * a * a / (2.0 * s2);        // c mu^2 / (2 sig2_beta) = bq s^2
             }

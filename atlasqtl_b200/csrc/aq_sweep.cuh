@@ -69,6 +69,14 @@ struct SweepParams {
     int rowpart_base;       // first row of this launch in rowpart
     int p_pad;
     int mode;               // 0: sweep;  1: build residual (R -= X beta) + sums from the loaded state
+    // Segmented sweep (nseg > 1; single-CTA configurations, cooperative launch): the SNP blocks of every tile are cut into
+    // nseg segments of seg_len blocks and the work units (segment s, tile) are dealt round-robin, segment-major, to the
+    // persistent CTAs, so a partly filled last round costs 1 / nseg of a round instead of a whole one.  Unit (s, tile)
+    // needs (s - 1, tile), which another CTA finished at an EARLIER position of its own list; the hand-off goes through
+    // the residual / column sums in global memory and seg_done[tile] (release / acquire at gpu scope).
+    int nseg;
+    int seg_len;
+    int* seg_done;          // [ntiles] segments completed per tile, zeroed before the launch (NULL iff nseg == 1)
     long long* timing;      // development only (-DAQ_TIMING): per-section cycle sums of the chain warp
 };
 
@@ -87,7 +95,12 @@ struct SweepCfg {
     static constexpr int kThreads = 16 * 32;  // warps 3 (chain) and 7 (helper) + 14 MMA warps (two of them on SMSP 3)
     static constexpr int kStages = 3;
     static constexpr size_t kTileDoubles = (size_t)kBlk * kXS + kTileTail;
-    static constexpr int kSps = 10;  // S-partial row stride (doubles): 8 SNP slots + 2 pad => conflict-free 16-byte accesses
+    // S tiles in shared memory ([trait][8 SNP slots], partials and sums alike): row stride 8 doubles, the four 16-byte
+    // pairs of a row XOR-swizzled by (trait >> 1) & 3 (sp_off), so that both the C-fragment stores of the MMA warps (lanes
+    // = 2 traits x 4 pairs per quarter-warp) and the row reads of the chain / helper (lanes = 8 consecutive traits, same
+    // pair) hit 8 different 16-byte bank groups.  (ncu on the unswizzled stride-10 layout: 2-way conflicts on every
+    // partial store, 15 % of the kernel's shared-memory wavefronts.)
+    static constexpr int kSps = 8;
     static constexpr size_t kSpartDoubles = (size_t)WS * kT * kSps;      // [WS][kT][kSps], single-buffered (sfree barrier)
     // who sums the split-K partials of S: the chain warp itself (single CTA: one hop less between the tensor work and the
     // recurrence), or the helper warp (clusters: the wait for the other CTAs' slices stays off the serial path)
@@ -112,6 +125,15 @@ struct SweepCfg {
     static_assert(kXS % 16 == 8, "row stride must be 8 mod 16 doubles");
     static_assert(kSmemBytes <= 232448, "shared memory budget (227 KB)");
 };
+
+// offset (doubles) of SNP slot t (even: the pair t, t + 1) of trait row r in an S tile
+__device__ __forceinline__ int sp_off(int r, int t) { return r * 8 + ((((t >> 1) ^ (r >> 1)) & 3) << 1) + (t & 1); }
+// offset (doubles) of (trait r, SNP slot t) in a -Delta block of kT traits: pair-major [t >> 1][trait][2] with bit 3
+// flipped in odd pair planes: the chain's 16-byte stores (lanes = consecutive traits) and the MMA warps' 8-byte loads
+// (lane (g, l) reads trait g, slot l and l + 4) are both bank-conflict free (the trait-major [trait][8] layout gave 4-way
+// conflicts on both)
+template <int kT>
+__device__ __forceinline__ int d_off(int r, int t) { return (t >> 1) * 2 * kT + ((2 * r + (t & 1)) ^ (((t >> 1) & 1) << 3)); }
 
 // Sums of N values per lane over a group of G consecutive lanes (G = 4 N), by recursive halving: at every step a lane
 // hands half of its values to its partner and keeps the other half.  On return v[0] of lane L is the group total of value
@@ -145,7 +167,6 @@ __device__ __forceinline__ void sum_s_partials(double (&s)[kBlk], const double* 
     constexpr int kH = (kT <= 16) ? 2 : 1;
     constexpr int kW0 = (WS + kH - 1) / kH;
     const int half = (kH == 2) ? (lane >> 4) : 0;
-    const double* sp0 = spart + tsum * Cfg::kSps;
 #pragma unroll
     for (int t = 0; t < kBlk; ++t) s[t] = 0.0;
 #pragma unroll
@@ -154,7 +175,7 @@ __device__ __forceinline__ void sum_s_partials(double (&s)[kBlk], const double* 
         if (kH == 1 || w < WS) {
 #pragma unroll
             for (int t = 0; t < kBlk; t += 2) {
-                const double2 v = *reinterpret_cast<const double2*>(sp0 + w * kT * Cfg::kSps + t);
+                const double2 v = *reinterpret_cast<const double2*>(spart + w * kT * Cfg::kSps + sp_off(tsum, t));
                 s[t] += v.x;
                 s[t + 1] += v.y;
             }
@@ -167,10 +188,10 @@ __device__ __forceinline__ void sum_s_partials(double (&s)[kBlk], const double* 
         mbar_wait(&sred[gb & 1], (uint32_t)((gb >> 1) & 1));
         if (half == 0) {
             for (int r2 = 1; r2 < ncta; ++r2) {
-                const double* rp = red + ((size_t)((gb & 1) * (kMaxCluster - 1) + (r2 - 1)) * kT + tsum) * Cfg::kSps;
+                const double* rp = red + (size_t)((gb & 1) * (kMaxCluster - 1) + (r2 - 1)) * kT * Cfg::kSps;
 #pragma unroll
                 for (int t = 0; t < kBlk; t += 2) {
-                    const double2 v = *reinterpret_cast<const double2*>(rp + t);
+                    const double2 v = *reinterpret_cast<const double2*>(rp + sp_off(tsum, t));
                     s[t] += v.x;
                     s[t + 1] += v.y;
                 }
@@ -183,6 +204,45 @@ __device__ __forceinline__ void sum_s_partials(double (&s)[kBlk], const double* 
     }
 }
 
+// One work unit of a persistent CTA (cluster): SNP blocks [b0, b1) of trait tile `tile` (= all blocks when nseg == 1).
+struct Unit {
+    int tile, seg, b0, b1;
+};
+__device__ __forceinline__ Unit unit_of(const SweepParams& P, int group, int ngroups, int ju) {
+    const int u = group + ju * ngroups;   // segment-major: (seg, tile) needs (seg - 1, tile) = unit u - ntiles < u
+    Unit w;
+    w.seg = u / P.ntiles;
+    w.tile = u - w.seg * P.ntiles;
+    w.b0 = w.seg * P.seg_len;
+    w.b1 = min(P.nb, w.b0 + P.seg_len);
+    return w;
+}
+// wait (one lane polls, acquire at gpu scope) until the previous segment of the unit's tile has been handed off
+__device__ __forceinline__ void unit_acquire(const SweepParams& P, const Unit& w, int lane) {
+    if (w.seg > 0) {
+        if (lane == 0) {
+            uint32_t spins = 0;
+            while (ld_acquire_gpu(P.seg_done + w.tile) < w.seg) {
+                __nanosleep(64);
+                if (++spins == kSpinLimit) __trap();
+            }
+        }
+        __syncwarp();
+    }
+}
+// end of a unit (segmented launches only): every warp of the CTA has finished its global writes of the unit -> publish
+template <class Cfg>
+__device__ __forceinline__ void unit_release(const SweepParams& P, const Unit& w) {
+    if (P.nseg > 1) {
+        __syncwarp();
+        asm volatile("bar.sync 2, %0;" ::"n"(Cfg::kThreads) : "memory");
+        if (threadIdx.x == 0) {
+            __threadfence();
+            st_release_gpu(P.seg_done + w.tile, w.seg + 1);
+        }
+    }
+}
+
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepParams P) {
     constexpr int WS = Cfg::WS, MT = Cfg::MT, NT = Cfg::NT, kT = Cfg::kT, XS = Cfg::kXS;
@@ -192,7 +252,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
     double* tiles = reinterpret_cast<double*>(smem_raw);
     double* spart = tiles + kStages * Cfg::kTileDoubles;  // [WS][kT][kSps]
     double* ssum = spart + Cfg::kSpartDoubles;            // [2][kT][kSps]  (clustered variant only)
-    double* dbuf = ssum + Cfg::kSsumDoubles;              // [2][kT][kBlk]  (holds -Delta)
+    double* dbuf = ssum + Cfg::kSsumDoubles;              // [2][kT x kBlk]  (holds -Delta, d_off layout)
     double* rsqs = dbuf + Cfg::kDbufDoubles;              // [WS][kT]
     double* iobuf = rsqs + Cfg::kRsqDoubles;              // [2][kBlk][2][kT]
     double* stg = iobuf + Cfg::kIoDoubles;                // [5][kBlk][kT]
@@ -223,7 +283,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
     const bool is_producer = mma_idx == Cfg::kMmaWarps - 1 && is_mma;      // also streams the X tiles
     const int ncta = kCl ? P.ncta : 1;
     const int rank = kCl ? (int)cluster_ctarank() : 0;
-    const int group = kCl ? (int)cluster_id_x() : (int)blockIdx.x;         // tile-loop index of this CTA (cluster)
+    const int group = kCl ? (int)cluster_id_x() : (int)blockIdx.x;         // unit-loop index of this CTA (cluster)
     const int ngroups = kCl ? (int)cluster_count_x() : (int)gridDim.x;
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], Cfg::kMmaWarps); }
@@ -242,22 +302,40 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
     if (kCl) cluster_sync_all();  // every CTA's barriers are initialised before any remote arrive
 
     const int nb = P.nb;
-    const int my_tiles = (P.ntiles - group + ngroups - 1) / ngroups;
-    const long total = (long)my_tiles * nb;
+    const int nunits = P.ntiles * P.nseg;
+    const int my_units = (nunits - group + ngroups - 1) / ngroups;
     const uint32_t tile_bytes = (uint32_t)(Cfg::kTileDoubles * sizeof(double));
 
     if (is_mma) {
         // ------------------------------------------------------------------ MMA warps
         const int ws = mma_idx;
         const int mtid = mma_idx * 32 + lane;
-        auto load_tile = [&](long it) {  // producer duty (one lane): X tile `it` of this CTA's stream into its ring stage
+        // producer duty (one lane): the X tiles of this CTA's units, in order, into the ring; (pj, pb) is its cursor
+        long total = 0;   // blocks this CTA sweeps
+        int pj = 0, pb = 0, pb1 = 0;
+        if (is_producer) {
+            for (int ju = 0; ju < my_units; ++ju) {
+                const Unit w = unit_of(P, group, ngroups, ju);
+                total += w.b1 - w.b0;
+            }
+            if (my_units > 0) {
+                const Unit w = unit_of(P, group, ngroups, 0);
+                pb = w.b0;
+                pb1 = w.b1;
+            }
+        }
+        auto load_next = [&](long it) {
             const int stage = (int)(it % kStages);
-            const int b = (int)(it % nb);
             mbar_arrive_expect_tx(&full[stage], tile_bytes);
-            bulk_g2s(tiles + stage * Cfg::kTileDoubles, P.xtiles + ((size_t)b * ncta + rank) * P.tile_stride, tile_bytes, &full[stage]);
+            bulk_g2s(tiles + stage * Cfg::kTileDoubles, P.xtiles + ((size_t)pb * ncta + rank) * P.tile_stride, tile_bytes, &full[stage]);
+            if (++pb == pb1 && ++pj < my_units) {
+                const Unit w = unit_of(P, group, ngroups, pj);
+                pb = w.b0;
+                pb1 = w.b1;
+            }
         };
         if (is_producer && lane == 0)
-            for (long it = 0; it < kStages && it < total; ++it) load_tile(it);
+            for (long it = 0; it < kStages && it < total; ++it) load_next(it);
         const int g = lane >> 2, l = lane & 3;
         const int i0 = ws * NT * 8;                       // first sample of this warp inside the CTA's slice
         const int ig = rank * Cfg::kNPad + i0;            // ... and inside the residual row
@@ -266,6 +344,8 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
         const int offS = g * XS + ((i0 + 2 * l) ^ ((g & 2) << 1));         // + nt*8   (16-byte loads)
         const int offU0 = l * XS + ((i0 + g) ^ ((l & 2) << 1));            // ks = 0, + nt*8
         const int offU1 = (l + 4) * XS + ((i0 + g) ^ ((l & 2) << 1));      // ks = 1 (snp l+4 has the same bit 1)
+        const int offD = d_off<kT>(tr0 + g, l);                            // -Delta[trait g][snp l]; + 16 mt, + 4 kT (snp l + 4)
+        const int offP = sp_off(tr0 + g, 2 * l);                           // S partial pair; + 64 mt
         uint32_t dcons_leader[2] = {0, 0}, rsqbar_leader = 0, rsq_all_leader = 0;
         if (kCl) {
             dcons_leader[0] = mapa_u32(&dcons[0], 0);
@@ -275,15 +355,16 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
         }
         double acc[MT][NT][2];
         long gb = 0;  // global block counter of this CTA (drives ring stage and barrier parity)
-        for (int ti = 0; ti < my_tiles; ++ti) {
-            const int tile = group + ti * ngroups;
-            const int k0 = P.k_base + tile * kT;
+        for (int ju = 0; ju < my_units; ++ju) {
+            const Unit un = unit_of(P, group, ngroups, ju);
+            const int k0 = P.k_base + un.tile * kT;
+            unit_acquire(P, un, lane);   // the residual of this tile as the previous segment left it
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
-                    const double2 v = *reinterpret_cast<const double2*>(
-                        P.resid + (size_t)(k0 + tr0 + mt * 8 + g) * P.ld_resid + ig + nt * 8 + 2 * l);
+                    const double2 v = __ldcg(reinterpret_cast<const double2*>(
+                        P.resid + (size_t)(k0 + tr0 + mt * 8 + g) * P.ld_resid + ig + nt * 8 + 2 * l));
                     acc[mt][nt][0] = v.x;
                     acc[mt][nt][1] = v.y;
                 }
@@ -310,21 +391,21 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 AQ_T(11);
                 if (gbi > 0) mbar_wait(&sfree[0], (uint32_t)((gbi - 1) & 1));  // the previous block's partials have been read
                 AQ_T(12);
-                double* sp = spart + (size_t)ws * kT * Cfg::kSps;
+                double* sp = spart + (size_t)ws * kT * Cfg::kSps + offP;
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
                     double2 v;  // C fragment: S^T[trait g + 8 mt][snp 2l, 2l + 1]
                     v.x = (kSC == 2) ? sa[mt][0][0] + sa[mt][1][0] : sa[mt][0][0];
                     v.y = (kSC == 2) ? sa[mt][0][1] + sa[mt][1][1] : sa[mt][0][1];
-                    *reinterpret_cast<double2*>(sp + (tr0 + mt * 8 + g) * Cfg::kSps + 2 * l) = v;
+                    *reinterpret_cast<double2*>(sp + mt * 8 * Cfg::kSps) = v;
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sdone[gbi & 1]);
                 AQ_T(13);
             };
             if (P.mode == 0) s_phase(gb);
-            for (int b = 0; b < nb; ++b, ++gb) {
-                if (P.mode == 0 && b + 1 < nb) s_phase(gb + 1);
+            for (int b = un.b0; b < un.b1; ++b, ++gb) {
+                if (P.mode == 0 && b + 1 < un.b1) s_phase(gb + 1);
                 // ---- rank-8 update with -Delta_b
                 const int stage = (int)(gb % kStages);
                 AQ_T0();
@@ -349,8 +430,8 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 double nd[MT][2];
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
-                    nd[mt][0] = db[(tr0 + mt * 8 + g) * kBlk + l];
-                    nd[mt][1] = db[(tr0 + mt * 8 + g) * kBlk + l + 4];
+                    nd[mt][0] = db[offD + 16 * mt];
+                    nd[mt][1] = db[offD + 16 * mt + 4 * kT];
                 }
                 if (P.mode != 0) {
                     // no S phase paces the chain in this mode: tell it that -Delta buffer (gb & 1) has been consumed,
@@ -388,12 +469,12 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 if (is_producer) {  // refill the stage once every MMA warp has released it
                     if (lane == 0 && gb + kStages < total) {
                         mbar_wait(&empty[stage], (uint32_t)((gb / kStages) & 1));
-                        load_tile(gb + kStages);
+                        load_next(gb + kStages);
                     }
                     __syncwarp();
                 }
             }
-            // ---- tile epilogue: store the residual, per-trait squared norms
+            // ---- unit epilogue: store the residual; after the last segment of the tile, the per-trait squared norms
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
                 double ss = 0.0;
@@ -410,6 +491,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 ss += __shfl_xor_sync(0xffffffffu, ss, 2);
                 if (l == 0) rsqs[ws * kT + tr0 + mt * 8 + g] = ss;
             }
+            const bool last_seg = un.seg == P.nseg - 1;
             asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kMmaWarps * 32) : "memory");
             if (mtid < 32 * ((kT + 31) / 32)) {  // whole warps, so that the elected arrive below is warp-uniform
                 double ss = 0.0;
@@ -418,21 +500,22 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     for (int w2 = 0; w2 < WS; ++w2) ss += rsqs[w2 * kT + mtid];
                 }
                 if (!kCl) {
-                    if (mtid < kT && k0 + mtid < P.q) P.rsq[k0 + mtid] = ss;
+                    if (last_seg && mtid < kT && k0 + mtid < P.q) P.rsq[k0 + mtid] = ss;
                 } else if (rank != 0) {
                     if (mtid < kT) st_cluster_f64(rsq_all_leader + (uint32_t)(((rank - 1) * kT + mtid) * sizeof(double)), ss);
                     // release.cluster arrive below is cumulative over the stores ordered before it by __syncwarp
                     __syncwarp();
                     if (mtid == 0) mbar_arrive_cluster(rsqbar_leader);
                 } else {
-                    if (ncta > 1) mbar_wait_cluster(&rsqbar[0], (uint32_t)(ti & 1));
+                    if (ncta > 1) mbar_wait_cluster(&rsqbar[0], (uint32_t)(ju & 1));
                     if (mtid < kT) {
                         for (int r2 = 1; r2 < ncta; ++r2) ss += rsq_all[(r2 - 1) * kT + mtid];  // fixed order: deterministic
-                        if (k0 + mtid < P.q) P.rsq[k0 + mtid] = ss;
+                        if (last_seg && k0 + mtid < P.q) P.rsq[k0 + mtid] = ss;
                     }
                 }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kMmaWarps * 32) : "memory");
+            unit_release<Cfg>(P, un);
         }
     } else if (is_chain && rank != 0) {
         // ------------------------------------------------------------------ follower CTA: S-tile reducer warp
@@ -449,42 +532,46 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
         const int tls = active ? tl : 0;
         const uint32_t red_leader = mapa_u32(red, 0);
         const uint32_t sred_leader[2] = {mapa_u32(&sred[0], 0), mapa_u32(&sred[1], 0)};
-        for (long gb = 0; gb < total; ++gb) {
-            if (gb >= 2) mbar_wait(&dready[gb & 1], (uint32_t)(((gb >> 1) - 1) & 1));  // the phase of block gb - 2 is over
-            if (lane == 0) mbar_arrive_expect_tx(&dready[gb & 1], Cfg::kDeltaBytes);
-            if (P.mode != 0) continue;
-            mbar_wait(&sdone[gb & 1], (uint32_t)((gb >> 1) & 1));
-            const double* sp = spart + tls * Cfg::kSps;
-            double s[kBlk];
+        long gb = 0;
+        for (int ju = 0; ju < my_units; ++ju) {
+            const Unit un = unit_of(P, group, ngroups, ju);
+            for (int b = un.b0; b < un.b1; ++b, ++gb) {
+                if (gb >= 2) mbar_wait(&dready[gb & 1], (uint32_t)(((gb >> 1) - 1) & 1));  // the phase of block gb - 2 is over
+                if (lane == 0) mbar_arrive_expect_tx(&dready[gb & 1], Cfg::kDeltaBytes);
+                if (P.mode != 0) continue;
+                mbar_wait(&sdone[gb & 1], (uint32_t)((gb >> 1) & 1));
+                double s[kBlk];
 #pragma unroll
-            for (int t = 0; t < kBlk; ++t) s[t] = 0.0;
+                for (int t = 0; t < kBlk; ++t) s[t] = 0.0;
 #pragma unroll
-            for (int w2 = 0; w2 < kW0; ++w2) {
-                const int w = half * kW0 + w2;
-                if (kH == 1 || w < WS) {
+                for (int w2 = 0; w2 < kW0; ++w2) {
+                    const int w = half * kW0 + w2;
+                    if (kH == 1 || w < WS) {
 #pragma unroll
-                    for (int t = 0; t < kBlk; t += 2) {
-                        const double2 v = *reinterpret_cast<const double2*>(sp + w * kT * Cfg::kSps + t);
-                        s[t] += v.x;
-                        s[t + 1] += v.y;
+                        for (int t = 0; t < kBlk; t += 2) {
+                            const double2 v = *reinterpret_cast<const double2*>(spart + w * kT * Cfg::kSps + sp_off(tls, t));
+                            s[t] += v.x;
+                            s[t + 1] += v.y;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sfree[0]);  // the MMA warps may overwrite the partials
+                if (kH == 2) {
+#pragma unroll
+                    for (int t = 0; t < kBlk; ++t) s[t] += __shfl_xor_sync(0xffffffffu, s[t], 16);
+                }
+                if (active) {
+                    const uint32_t dst = red_leader + (uint32_t)((((gb & 1) * (kMaxCluster - 1)) + (rank - 1)) * kT *
+                                                                 Cfg::kSps * sizeof(double));
+#pragma unroll
+                    for (int i = 0; i < kTP; i += 2) {
+                        const int t = half * kTP + i;
+                        st_async_v2(dst + (uint32_t)sp_off(tl, t) * (uint32_t)sizeof(double), s[t], s[t + 1], sred_leader[gb & 1]);
                     }
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sfree[0]);  // the MMA warps may overwrite the partials
-            if (kH == 2) {
-#pragma unroll
-                for (int t = 0; t < kBlk; ++t) s[t] += __shfl_xor_sync(0xffffffffu, s[t], 16);
-            }
-            if (active) {
-                const uint32_t dst = red_leader + (uint32_t)(((((gb & 1) * (kMaxCluster - 1)) + (rank - 1)) * kT + tl) *
-                                                             Cfg::kSps * sizeof(double));
-#pragma unroll
-                for (int i = 0; i < kTP; i += 2) {
-                    const int t = half * kTP + i;
-                    st_async_v2(dst + t * (uint32_t)sizeof(double), s[t], s[t + 1], sred_leader[gb & 1]);
-                }
-            }
+            unit_release<Cfg>(P, un);
         }
     } else if (is_helper) {
         // ------------------------------------------------------------------ helper warp (leader CTA, sweep mode)
@@ -493,22 +580,24 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
         // one block earlier, so no HBM / L2 latency sits between "S is complete" and "the chain may start") and the
         // split-K partials of S are summed; after the chain, gam / mu go back to HBM and the per-trait running sums
         // are accumulated.  With <= 16 traits per tile the two half-warps split the work.
-        if (P.mode == 0 && rank == 0) {
-            constexpr int kH = (kT <= 16) ? 2 : 1;
-            constexpr int kTP = kBlk / kH;           // SNP slots per lane
-            // W / I0 of a block: staged with the other rows when a lane handles 4 SNP slots; with 8 slots per lane (T > 16)
-            // the extra asynchronous copies cost more than they hide, and W / I0 are requested directly one block ahead
-            constexpr bool kStageWI = (kH == 2);
-            const int half = (kH == 2) ? (lane >> 4) : 0;
-            const int tl = (kH == 2) ? (lane & 15) : lane;
-            const bool active = tl < kT;
-            const int tls = active ? tl : 0;
-            const int t0 = half * kTP;
-            int idn[kTP], idc[kTP];
-            double wn[kTP], in[kTP];   // W, I0 of the block being prepared: consumed after its chain
-            long gb = 0;
-            for (int ti = 0; ti < my_tiles; ++ti) {
-                const int tile = group + ti * ngroups;
+        constexpr int kH = (kT <= 16) ? 2 : 1;
+        constexpr int kTP = kBlk / kH;           // SNP slots per lane
+        // W / I0 of a block: staged with the other rows when a lane handles 4 SNP slots; with 8 slots per lane (T > 16)
+        // the extra asynchronous copies cost more than they hide, and W / I0 are requested directly one block ahead
+        constexpr bool kStageWI = (kH == 2);
+        const int half = (kH == 2) ? (lane >> 4) : 0;
+        const int tl = (kH == 2) ? (lane & 15) : lane;
+        const bool active = tl < kT;
+        const int tls = active ? tl : 0;
+        const int t0 = half * kTP;
+        const bool work = P.mode == 0 && rank == 0;
+        int idn[kTP], idc[kTP];
+        double wn[kTP], in[kTP];   // W, I0 of the block being prepared: consumed after its chain
+        long gb = 0;
+        for (int ju = 0; ju < my_units; ++ju) {
+            const Unit un = unit_of(P, group, ngroups, ju);
+            if (work) {
+                const int tile = un.tile;
                 const int k = P.k_base + tile * kT + tls;
                 const bool valid = active && k < P.q;
                 const double sig2 = P.sig2_beta[k];
@@ -556,7 +645,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                             io[(t * 2 + 1) * kT + tl] = P.c * (dd + cst);              // :75-77 without the mu^2 term
                         }
                     }
-                    if (blk + 1 < nb) stage_rows(blk + 1);
+                    if (blk + 1 < un.b1) stage_rows(blk + 1);
                     if (!Cfg::kChainSums) {
                         mbar_wait(&sdone[g & 1], (uint32_t)((g >> 1) & 1));
                         AQ_T(4);
@@ -568,7 +657,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                                 double2 v;
                                 v.x = s[t];
                                 v.y = s[t + 1];
-                                *reinterpret_cast<double2*>(ssum + ((size_t)(g & 1) * kT + tl) * Cfg::kSps + t) = v;
+                                *reinterpret_cast<double2*>(ssum + (size_t)(g & 1) * kT * Cfg::kSps + sp_off(tl, t)) = v;
                             }
                         }
                     }
@@ -616,9 +705,9 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     }
                     AQ_T(9);
                 };
-                stage_rows(0);
-                pre(gb, 0);
-                for (int b = 0; b < nb; ++b, ++gb) {
+                stage_rows(un.b0);
+                pre(gb, un.b0);
+                for (int b = un.b0; b < un.b1; ++b, ++gb) {
                     double ww[kTP], ii[kTP];
 #pragma unroll
                     for (int i = 0; i < kTP; ++i) {
@@ -632,7 +721,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                             ii[i] = P.i0tab[off];
                         }
                     }
-                    if (b + 1 < nb) pre(gb + 1, b + 1);
+                    if (b + 1 < un.b1) pre(gb + 1, b + 1);
                     post(gb, ww, ii);
                 }
                 if (kH == 2) {
@@ -641,13 +730,21 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     sb2 += __shfl_xor_sync(0xffffffffu, sb2, 16);
                     sz += __shfl_xor_sync(0xffffffffu, sz, 16);
                 }
+                unit_acquire(P, un, lane);   // the column sums of the earlier segments (fixed order: deterministic)
                 if (valid && half == 0) {
+                    if (un.seg > 0) {
+                        sg += __ldcg(P.cs_gam + k);
+                        sgm2 += __ldcg(P.cs_gmu2 + k);
+                        sb2 += __ldcg(P.cs_b2 + k);
+                        sz += __ldcg(P.cs_z + k);
+                    }
                     P.cs_gam[k] = sg;
                     P.cs_gmu2[k] = sgm2;
                     P.cs_b2[k] = sb2;
                     P.cs_z[k] = sz;
                 }
             }
+            unit_release<Cfg>(P, un);
         }
     } else if (is_chain) {
         // ------------------------------------------------------------------ chain warp (one lane per trait; leader CTA)
@@ -668,16 +765,16 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     double2 v;
                     v.x = nd[t];
                     v.y = nd[t + 1];
-                    *reinterpret_cast<double2*>(dblk + tl * kBlk + t) = v;
+                    *reinterpret_cast<double2*>(dblk + d_off<kT>(tl, t)) = v;
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&dready[gb & 1]);
         };
         long gb = 0;
-        for (int ti = 0; ti < my_tiles; ++ti) {
-            const int tile = group + ti * ngroups;
-            const int k = P.k_base + tile * kT + tls;
+        for (int ju = 0; ju < my_units; ++ju) {
+            const Unit un = unit_of(P, group, ngroups, ju);
+            const int k = P.k_base + un.tile * kT + tls;
             const bool valid = active && k < P.q;
             if (P.mode == 0) {
                 // ---- sweep: only the serial recurrence lives here; inputs arrive through shared memory (helper warp)
@@ -687,7 +784,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 double corr[kBlk];  // look-ahead correction of the NEXT block, accumulated while this one is resolved
 #pragma unroll
                 for (int t = 0; t < kBlk; ++t) corr[t] = 0.0;
-                for (int b = 0; b < nb; ++b, ++gb) {
+                for (int b = un.b0; b < un.b1; ++b, ++gb) {
                     AQ_T0();
                     const int stage = (int)(gb % kStages);
                     mbar_wait(&full[stage], (uint32_t)((gb / kStages) & 1));
@@ -708,10 +805,10 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                         sum_s_partials<Cfg>(s, spart, red, sfree, sred, gb, ncta, lane, tsum);
                     } else {
                         AQ_T(0);
-                        const double* sp0 = ssum + ((size_t)(gb & 1) * kT + tsum) * Cfg::kSps;
+                        const double* sp0 = ssum + (size_t)(gb & 1) * kT * Cfg::kSps;
 #pragma unroll
                         for (int t = 0; t < kBlk; t += 2) {
-                            const double2 v = *reinterpret_cast<const double2*>(sp0 + t);
+                            const double2 v = *reinterpret_cast<const double2*>(sp0 + sp_off(tsum, t));
                             s[t] = v.x;
                             s[t + 1] = v.y;
                         }
@@ -748,7 +845,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
             } else {
                 // ---- mode 1: R = Y - X beta from the loaded state, and its per-trait sums
                 double sg = 0.0, sgm2 = 0.0, sb2 = 0.0;
-                for (int b = 0; b < nb; ++b, ++gb) {
+                for (int b = un.b0; b < un.b1; ++b, ++gb) {
                     const int stage = (int)(gb % kStages);
                     mbar_wait(&full[stage], (uint32_t)((gb / kStages) & 1));
                     const int* ids = reinterpret_cast<const int*>(tiles + stage * Cfg::kTileDoubles + kBlk * XS + 128);
@@ -772,12 +869,19 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     }
                     publish(gb, nd);
                 }
+                unit_acquire(P, un, lane);
                 if (valid) {
+                    if (un.seg > 0) {
+                        sg += __ldcg(P.cs_gam + k);
+                        sgm2 += __ldcg(P.cs_gmu2 + k);
+                        sb2 += __ldcg(P.cs_b2 + k);
+                    }
                     P.cs_gam[k] = sg;
                     P.cs_gmu2[k] = sgm2;
                     P.cs_b2[k] = sb2;
                 }
             }
+            unit_release<Cfg>(P, un);
         }
     }
 #ifdef AQ_TIMING

@@ -197,6 +197,12 @@ class SweepContext:
     def launch_count(self):
         return int(self._lib.aq_launch_count(self._ctx))
 
+    def sweep_plan(self):
+        """How the last sweep spread its trait tiles over the GPU (aq_sweep_plan)."""
+        v = [ctypes.c_int() for _ in range(4)]
+        _lib.check(self._lib.aq_sweep_plan(self._ctx, *[ctypes.byref(x) for x in v]))
+        return dict(zip(("traits_per_tile", "ntiles", "groups", "nseg"), (x.value for x in v)))
+
     def last_sweep_ms(self):
         ms = ctypes.c_float()
         _lib.check(self._lib.aq_last_sweep_ms(self._ctx, ctypes.byref(ms)))

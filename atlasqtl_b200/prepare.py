@@ -28,7 +28,26 @@ def rm_collinear_(X_scaled, names):
     return X_scaled[:, ~bool_coll], bool_coll, rmvd
 
 
-def prepare_data_(Y, X, tol, maxit, user_seed=None, verbose=0):
+def check_common_(Y, n, tol, maxit, checkpoint_path=None):
+    """The argument checks shared by the host and device pre-processing (R/prepare_atlasqtl.R:11-45)."""
+    import os
+    if not (tol > 0):
+        raise ValueError("tol must be positive.")
+    if not (maxit >= 1 and int(maxit) == maxit):
+        raise ValueError("maxit must be a natural number.")
+    if checkpoint_path is not None and not os.path.isdir(os.path.dirname(checkpoint_path) or "."):  # :20-22 (path is a prefix)
+        raise ValueError("The directory specified in checkpoint_path does not exist. Please make sure to provide a "
+                         "valid path.")
+    if Y.shape[0] != n:
+        raise ValueError("X and Y must have the same number of samples.")
+    obs = ~np.isnan(Y)
+    if obs.sum() / Y.size < 0.05:  # :39-40
+        raise ValueError("Too few non-NA values in matrix Y. Exit.")
+    if (obs.sum(axis=0) / n < 0.025).any():  # :42-45
+        raise ValueError("Column(s) of matrix Y have more than 97.5% missing values, and should be removed. Exit.")
+
+
+def prepare_data_(Y, X, tol, maxit, user_seed=None, verbose=0, checkpoint_path=None):
     """Returns dict(Y, X, bool_rmvd_x, initial_colnames_X, rmvd_cst_x, rmvd_coll_x, names_x, names_y)."""
     X = np.asarray(X, dtype=np.float64)
     Y = np.asarray(Y, dtype=np.float64)
@@ -37,14 +56,9 @@ def prepare_data_(Y, X, tol, maxit, user_seed=None, verbose=0):
     n, p = X.shape
     if n < 2:
         raise ValueError("X must have at least 2 rows.")  # check_structure_/check dims, :11-30
-    if Y.shape[0] != n:
-        raise ValueError("X and Y must have the same number of samples.")
+    check_common_(Y, n, tol, maxit, checkpoint_path)
     if np.isnan(X).any():
         raise ValueError("X must not contain missing values.")
-    if not (tol > 0):
-        raise ValueError("tol must be positive.")
-    if not (maxit >= 1 and int(maxit) == maxit):
-        raise ValueError("maxit must be a natural number.")
     names_x = [f"Cov_x_{j + 1}" for j in range(p)]  # :54
     names_y = [f"Resp_{k + 1}" for k in range(Y.shape[1])]  # :55
     with np.errstate(invalid="ignore", divide="ignore"):
@@ -63,7 +77,7 @@ def prepare_data_(Y, X, tol, maxit, user_seed=None, verbose=0):
                 names_y=names_y)
 
 
-def prepare_data_device_(Y, X, tol, maxit, user_seed=None, verbose=0, *, packed_n=None, device=0):
+def prepare_data_device_(Y, X, tol, maxit, user_seed=None, verbose=0, checkpoint_path=None, *, packed_n=None, device=0):
     """`prepare_data_` with the O(np) work on the GPU (include/atlasqtl_b200.h, aq_prep_x / aq_prep_geno): same
     checks, same returned fields, except that "X" is a `PreparedPredictors` handle (the standardised matrix exists
     only on the device) and "Y" is the RAW response matrix, centred on the device when the context is created.
@@ -72,18 +86,8 @@ def prepare_data_device_(Y, X, tol, maxit, user_seed=None, verbose=0, *, packed_
     Y = np.asarray(Y, dtype=np.float64)
     if Y.ndim != 2:
         raise ValueError("X and Y must be matrices.")
-    if not (tol > 0):
-        raise ValueError("tol must be positive.")
-    if not (maxit >= 1 and int(maxit) == maxit):
-        raise ValueError("maxit must be a natural number.")
     n = int(packed_n) if packed_n is not None else np.shape(X)[0]
-    if Y.shape[0] != n:
-        raise ValueError("X and Y must have the same number of samples.")
-    obs = ~np.isnan(Y)
-    if obs.sum() / Y.size < 0.05:  # R/prepare_atlasqtl.R:39-40
-        raise ValueError("Too few non-NA values in matrix Y. Exit.")
-    if (obs.sum(axis=0) / n < 0.025).any():  # :42-45
-        raise ValueError("Column(s) of matrix Y have more than 97.5% missing values, and should be removed. Exit.")
+    check_common_(Y, n, tol, maxit, checkpoint_path)
     prep = PreparedPredictors(packed=X, n=n, device=device) if packed_n is not None else PreparedPredictors(X, device=device)
     if prep.p < 1:
         raise ValueError("There must be at least 1 non-constant candidate predictor stored in X.")

@@ -88,6 +88,7 @@ typedef struct aq_prep aq_prep;
 int aq_prep_x(aq_prep** out, int device, int n, int p_raw, const double* X_raw, int* p_kept);
 int aq_prep_geno(aq_prep** out, int device, int n, int p_raw, const uint8_t* geno, int64_t bytes_per_col, int* p_kept);
 int aq_prep_result(const aq_prep* prep, uint8_t* status, int32_t* dup_of, double* mean, double* sd);
+int aq_prep_dims(const aq_prep* prep, int* n, int* p_raw, int* p_kept);   /* any pointer may be NULL */
 int aq_prep_destroy(aq_prep* prep);
 int64_t aq_prep_launch_count(const aq_prep* prep);
 int aq_create_prepared(aq_ctx** out, const aq_prep* prep, int q_local, const double* Y_raw, double* n_obs);
@@ -239,6 +240,34 @@ int aq_coreDualLoop(int device, int p, int q, const double* cp_X, const double* 
                     double log_sig2_inv_vb, const double* log_tau_vb, double* m1_beta, double* cp_betaX_X,
                     double* mu_beta_vb, const double* sig2_beta_vb, const double* tau_vb,
                     const int32_t* shuffled_ind, int n_ind, const int32_t* sample_q, int n_q, double c);
+
+
+/*
+ * Same for the missing-response entry point: the 16 arguments of coreDualMisLoop (src/coreLoop.cpp:91-106; .Call glue
+ * src/RcppExports.cpp:41-63).  cp_X_rm is the R list of q p x p matrices crossprod(X[missing rows of trait k, ])
+ * (R/atlasqtl_global_local_core.R:25-32) as an array of q pointers; sig2_beta_vb is p x q.  In-place outputs as above.
+ * Every trait needs its own factorisation of cp_X - cp_X_rm[[k]]: compatibility / parity entry for small p and q.
+ */
+int aq_coreDualMisLoop(int device, int p, int q, const double* cp_X, const double* const* cp_X_rm, const double* cp_Y_X,
+                       double* gam_vb, const double* log_Phi_theta_plus_zeta,
+                       const double* log_1_min_Phi_theta_plus_zeta, double log_sig2_inv_vb, const double* log_tau_vb,
+                       double* m1_beta, double* cp_betaX_X, double* mu_beta_vb, const double* sig2_beta_vb,
+                       const double* tau_vb, const int32_t* shuffled_ind, int n_ind, const int32_t* sample_q, int n_q,
+                       double c);
+
+/*
+ * How the last aq_sweep spread its trait tiles over the GPU: traits per tile, tiles, tiles a round of the persistent
+ * grid processes (SMs or schedulable clusters), and the number of SNP segments every tile was cut into (1 = each CTA
+ * sweeps all SNPs of its tiles; > 1 = segmented sweep).  Any pointer may be NULL.
+ */
+int aq_sweep_plan(const aq_ctx* ctx, int* traits_per_tile, int* ntiles, int* groups, int* nseg);
+
+/*
+ * Test hook: out[i] = the sweep's annealed logistic 1 / (1 + exp(x[i])) evaluated ON THE DEVICE with the very routine
+ * the chain warp uses (== exp(-logOnePlusExp(x)), src/coreLoop.cpp:28-33, :75-77), so that its range handling
+ * (|x| > 700, NaN) can be checked directly.  x, out: host arrays of length n.
+ */
+int aq_test_logistic(int device, const double* x, double* out, int n);
 
 #ifdef __cplusplus
 }

@@ -55,3 +55,27 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 assert not pat.search(open(os.path.join(dirpath, f)).read()), f
+
+
+def test_r_shim_compiles_against_the_c_abi():
+    """bindings/R/atlasqtl_b200_shim.c cannot be built against R here (no R headers); it is syntax- and type-checked
+    against stand-in declarations of the R API names it uses (tests/r_stub) and the real include/atlasqtl_b200.h, and
+    every C-ABI call in it must name an exported symbol.  Every wrapper that hands a pointer to the library validates
+    the SEXP first (unchecked sizes)."""
+    import subprocess
+    shim = os.path.join(ROOT, "bindings", "R", "atlasqtl_b200_shim.c")
+    res = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-Wno-cast-function-type",
+                          "-I", os.path.join(ROOT, "tests", "r_stub"), "-I", os.path.join(ROOT, "include"), shim],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    text = re.sub(r"/\*.*?\*/", "", open(shim).read(), flags=re.S)
+    used = set(re.findall(r"\b(aq_[a-zA-Z0-9_]+)\s*\(", text)) - {"aq_ctx", "aq_prep"}
+    assert used <= set(declared_symbols()), used - set(declared_symbols())
+    # the two .Call symbols of the reference (src/RcppExports.cpp:65-69) are registered with their arities
+    assert re.search(r'"_atlasqtl_coreDualLoop",[^}]*15\}', text) and re.search(r'"_atlasqtl_coreDualMisLoop",[^}]*16\}', text)
+    # no raw REAL()/INTEGER() of a caller-supplied argument reaches the library without a check, except the in-place
+    # gam_vb of the stateless entries (whose dims define p, q and are checked to be a double matrix) and X / Y of aq_create
+    for m in re.finditer(r"check\(aq_[a-z_A-Z]+\((.*?)\)\);", text, flags=re.S):
+        args = m.group(1)
+        raw = re.findall(r"\b(?:REAL|INTEGER)\((\w+)\)", args)
+        assert set(raw) <= {"gam_vb", "X", "Y", "v", "n_obs"}, (m.group(0)[:60], raw)

@@ -1,0 +1,85 @@
+"""GPU: full VB runs at the BASELINE.json shapes against committed golden trajectories of the CPU oracle
+(tests/golden/make_trajectory.py): ELBO at every evaluated iteration, iteration count at convergence, the PPI > 0.5 and
+bFDR < 0.05 selection sets (R/summarise_output.R:99-106, :207-223; convergence logic R/atlasqtl_global_local_core.R:342-375).
+
+  C1  n=200, p=500, q=1000, no annealing   golden from the reference's own coreLoop.cpp inside the restated R loop; also
+                                           re-run live on the box against oracle/_ref (src/coreLoop.cpp:38-86 as is)
+  C4  n=500, p=10000, q=5000, 20 hotspots, anneal=c(1,2,10)   the config north_star designates for trajectory / selection
+                                           parity; golden from the primal restatement (its p x p Gram is 0.8 GB and one
+                                           dual sweep 5e11 flop-pairs), ~35 CPU-minutes, so golden only
+
+Bars: max|d gam_vb| <= 1e-8, max|d beta_vb| <= 1e-8, ELBO relative <= 1e-10 at every evaluated
+iteration, identical iteration count, identical index sets -- on the host from the downloaded gam_vb with the ORACLE's
+assign_bFDR, and on the device with select_ppi_device / select_bFDR_device."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+
+def _run_and_compare(name, live_reference=False):
+    import make_trajectory as mt
+    from atlasqtl_b200 import core, summarise
+    from atlasqtl_b200.device import SweepContext
+    from oracle import vb_oracle
+    path = os.path.join(HERE, "golden", f"{name.lower()}_trajectory.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} has not been generated")
+    gold = np.load(path)
+    X, Y, hyper, init, anneal = mt.problem(name)
+    p, q = X.shape[1], Y.shape[1]
+    # same inputs as the golden run? (NumPy generator streams and brentq are deterministic; this tells drift from a bug)
+    np.testing.assert_allclose(mt.input_checksums(X, Y, hyper, init), gold["in_check"], rtol=1e-12)
+    trace = []
+    with SweepContext(X, Y) as ctx:
+        out = core.atlasqtl_global_local_core_(Y, X, q, anneal, 1, float(gold["tol"]), 1000, 0, hyper, init, debug=True,
+                                               trace=trace, ctx=ctx)
+        rows_p, cols_p = summarise.select_ppi_device(ctx, 0.5)
+        rows_f, cols_f, nsel = summarise.select_bFDR_device(ctx, 0.05)
+    assert out["converged"] and bool(gold["converged"])
+    assert out["it"] == int(gold["it"])
+    lb_it = np.array([r["it"] for r in trace if r["lb"] is not None])
+    lb = np.array([r["lb"] for r in trace if r["lb"] is not None])
+    assert np.array_equal(lb_it, gold["lb_it"])
+    rel = np.abs(lb - gold["lb"]) / np.abs(gold["lb"])
+    assert rel.max() <= 1e-10, rel.max()
+    gam_flat = out["gam_vb"].flatten(order="F")
+    assert np.abs(gam_flat[gold["probe_idx"]] - gold["probe_gam"]).max() <= 1e-8
+    assert np.abs(out["beta_vb"].flatten(order="F")[gold["probe_idx"]] - gold["probe_beta"]).max() <= 1e-8
+    assert abs(gam_flat.sum() - float(gold["sum_gam"])) <= 1e-9 * p * q   # every entry within 1e-9 on average
+    np.testing.assert_allclose(out["theta_vb"], gold["theta_vb"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(out["zeta_vb"], gold["zeta_vb"], rtol=1e-8, atol=1e-9)
+    # integer outputs, exact: host-side sets with the oracle's assign_bFDR ...
+    assert np.array_equal(np.flatnonzero(gam_flat > 0.5), gold["sel_ppi"])
+    assert np.array_equal(np.flatnonzero(vb_oracle.assign_bFDR(out["gam_vb"]).flatten(order="F") < 0.05), gold["sel_fdr"])
+    # ... and the sets formed on the device without downloading gam_vb
+    assert np.array_equal(np.sort(rows_p + cols_p * p), gold["sel_ppi"])
+    assert nsel == len(gold["sel_fdr"])
+    assert np.array_equal(np.sort(rows_f + cols_f * p), gold["sel_fdr"])
+    if live_reference:
+        from oracle import native
+        if not native.ref_available():
+            pytest.skip("oracle/_ref (the reference's coreLoop.cpp) is not available on this box")
+        tr_o = []
+        ref = vb_oracle.atlasqtl_global_local_core_(Y, X, q, anneal, 1, float(gold["tol"]), 1000, hyper, init,
+                                                    sweep="reference", trace=tr_o)
+        assert ref["it"] == out["it"]
+        for a, b in zip(tr_o, trace):
+            if a["lb"] is not None:
+                assert abs(a["lb"] - b["lb"]) <= 1e-10 * abs(a["lb"])
+        assert np.abs(ref["gam_vb"] - out["gam_vb"]).max() <= 1e-8
+        assert np.abs(ref["beta_vb"] - out["beta_vb"]).max() <= 1e-8
+        assert np.array_equal(ref["gam_vb"] > 0.5, out["gam_vb"] > 0.5)
+
+
+def test_c1_full_run_matches_golden_and_live_reference(oracle_built):
+    _run_and_compare("C1", live_reference=True)
+
+
+def test_c4_trajectory_and_selection_match_golden():
+    _run_and_compare("C4")

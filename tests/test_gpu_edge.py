@@ -218,7 +218,9 @@ def test_selection_sets_on_device_match_assign_bFDR(thres):
         rows, cols = summarise.select_ppi_device(ctx, thres)
         assert np.array_equal(np.stack([rows, cols], 1), np.argwhere(gam.T > thres)[:, ::-1])
         rows, cols, nsel = summarise.select_bFDR_device(ctx, thres)
-    want = summarise.assign_bFDR(gam) < thres
+    from oracle import vb_oracle
+    want = vb_oracle.assign_bFDR(gam) < thres   # the oracle's restatement of R/summarise_output.R:207-223, not product code
+    assert np.array_equal(want, summarise.assign_bFDR(gam) < thres)
     got = np.zeros_like(want)
     got[rows, cols] = True
     assert nsel == want.sum() == len(rows)
@@ -241,7 +243,53 @@ def test_bfdr_device_ties_at_the_boundary():
         with SweepContext(X, Y) as ctx:
             ctx.set_state(np.asfortranarray(gam), np.zeros((p, q)))
             rows, cols, nsel = summarise.select_bFDR_device(ctx, thres)
-        want = summarise.assign_bFDR(gam) < thres
+        from oracle import vb_oracle
+        want = vb_oracle.assign_bFDR(gam) < thres
         got = np.zeros_like(want)
         got[rows, cols] = True
         assert np.array_equal(got, want), thres
+
+
+@pytest.mark.parametrize("margin", [1e-9, -1e-9, 1e-12, -1e-12])
+def test_bfdr_device_near_threshold_boundary(margin):
+    """Adversarial: the running mean of 1 - PPI reaches thres -+ margin exactly at one element.  The reference decides with
+    a sequential cumsum / rank < thres (R/summarise_output.R:216-218); the device path with fixed-order tree sums of the same
+    terms.  The two can only disagree when |mean - thres| is at the rounding level of a sum of N terms (~N * 1e-16 * thres);
+    down to a relative margin of 1e-12 (N = 4800 here) the sets must be identical.  Checked against an exactly rounded
+    evaluation (math.fsum) and the oracle's assign_bFDR."""
+    import math
+
+    from atlasqtl_b200 import summarise
+    from atlasqtl_b200.device import SweepContext
+    from oracle import vb_oracle
+    rng = np.random.default_rng(21)
+    n, p, q = 30, 120, 40
+    thres = 0.05
+    X = np.asfortranarray(rng.normal(size=(n, p)))
+    Y = np.asfortranarray(rng.normal(size=(n, q)))
+    e = np.sort(rng.uniform(size=p * q) ** 3)   # 1 - PPI, ascending = decreasing PPI; distinct with probability 1
+    # find the prefix whose mean is closest below thres, then move its LAST element so that the mean lands at thres (1 + margin)
+    cs = np.cumsum(e) / np.arange(1, e.size + 1)
+    m = int(np.searchsorted(cs, thres))          # cs[m - 1] < thres <= cs[m]
+    assert 50 < m < e.size - 50
+    target = thres * (1 + margin) * (m + 1) - math.fsum(e[:m])
+    assert e[m - 1] < target < e[m + 1]
+    e[m] = target
+    assert np.all(np.diff(e) > 0)
+    gam = np.asfortranarray((1 - e)[rng.permutation(e.size)].reshape(p, q))
+    ee = np.sort(1 - gam.flatten())              # what the device actually sees (1 - (1 - e) is not e in general)
+    exact_mean = lambda k: math.fsum(ee[:k]) / k
+    k_sel = 0
+    while k_sel < ee.size and exact_mean(k_sel + 1) < thres:
+        k_sel += 1
+    if abs(exact_mean(m + 1) / thres - 1) < 1e-14:
+        pytest.skip("rounding of 1 - gam moved the constructed mean onto the threshold itself")
+    with SweepContext(X, Y) as ctx:
+        ctx.set_state(gam, np.zeros((p, q)))
+        rows, cols, nsel = summarise.select_bFDR_device(ctx, thres)
+    want = vb_oracle.assign_bFDR(gam) < thres
+    assert want.sum() == k_sel == (m + 1 if margin < 0 else m)
+    got = np.zeros_like(want)
+    got[rows, cols] = True
+    assert nsel == k_sel
+    assert np.array_equal(got, want)
