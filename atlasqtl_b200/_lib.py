@@ -15,7 +15,7 @@ EXPORTS = ["aq_last_error", "aq_version", "aq_device_info", "aq_create", "aq_des
            "aq_set_missing", "aq_set_state_mis", "aq_sweep_mis", "aq_ppi_count_sum", "aq_ppi_next_above", "aq_ppi_collect",
            "aq_prep_x", "aq_prep_geno", "aq_prep_result", "aq_prep_destroy", "aq_prep_launch_count", "aq_create_prepared",
            "aq_get_x", "aq_get_y", "aq_snapshot", "aq_snapshot_fetch", "aq_coreDualMisLoop", "aq_sweep_plan",
-           "aq_test_logistic", "aq_prep_dims"]
+           "aq_test_logistic", "aq_prep_dims", "aq_release_x"]
 
 
 class AtlasqtlB200Error(RuntimeError):

@@ -51,17 +51,26 @@ def _background():
     return _BG
 
 
+def _host_threads():
+    """Host threads this process may use for the p-vector special functions: its share of the box's cores when several
+    ranks run side by side (torchrun exports LOCAL_WORLD_SIZE); 8 ranks x 32 threads on a 32-core host made every rank
+    wait for the horseshoe update (round 1: hs_wait 1.1 ms per iteration at 8 GPUs)."""
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    share = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    return max(1, min(32, ncpu // share))
+
+
 def _pmap(fn, x, min_chunk=4096):
     """Apply an element-wise SciPy special function over a long p-vector on all host threads (the ufunc inner loops
     release the GIL).  These are the only non-trivial host costs per iteration: exp1 / gammaincc at p = 50k take
     tens of milliseconds single-threaded, comparable to the GPU sweep once the traits are spread over 8 GPUs."""
     global _POOL
     x = np.ascontiguousarray(x)
-    nthr = min(os.cpu_count() or 1, 32, max(1, x.size // min_chunk))
+    nthr = min(_host_threads(), max(1, x.size // min_chunk))
     if nthr <= 1:
         return fn(x)
     if _POOL is None:
-        _POOL = ThreadPoolExecutor(min(os.cpu_count() or 1, 32))
+        _POOL = ThreadPoolExecutor(_host_threads())
     out = np.empty_like(x, dtype=np.float64)
     bounds = np.linspace(0, x.size, nthr + 1).astype(int)
 
@@ -247,7 +256,7 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
                                 checkpoint_path=None, trace_path=None, full_output=False,
                                 thinned_elbo_eval=True, debug=False, batch="y", *, comm=None, slab=None,
                                 device=0, context_factory=None, order_fn=None, trace=None, ctx=None, iter_hook=None,
-                                checkpoint_rate=100, keep_checkpoints=False):
+                                checkpoint_rate=100, keep_checkpoints=False, release_x=None):
     """Same positional arguments as the reference core (R/atlasqtl_global_local_core.R:8-13).
 
     Y is THIS process's slab of responses (all of Y when comm is None); `slab` = (k_first, k_last)
@@ -255,6 +264,7 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
     (length q_total) can be sliced.  `order_fn(it, p)` supplies shuffled_ind per iteration (identity
     by default, like the reference, :162).  Keyword-only arguments are extensions; the R-facing ones
     keep their meaning.  Missing values in Y (NaN) select the coreDualMisLoop path (:19-38, :172-175), n <= 2048.
+    release_x: free the context's untiled copy of X once the state is set up (default: only for a context this call owns).
     """
     if batch != "y":
         raise ValueError("Batch scheme not defined. Exit.")  # only the C++ path is replaced (:179-232)
@@ -339,6 +349,10 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
             sums["colsum_m2"] = sums["colsum_gam_mu2"] + sig2_beta_vb * sums["colsum_gam"]
             sums["colsum_xn_m2"] = sums["colsum_xn_gam_mu2"] + sig2_beta_vb * sums["colsum_xn_gam"]
         del gam0, mu0
+        if release_x is None:
+            release_x = own_ctx   # a caller-owned context may be reused with another order / with missing responses
+        if release_x and order_fn is None and mis_pat is None and hasattr(ctx, "release_x"):
+            ctx.release_x()  # identity order for the whole run (:162) and no NA kernel: the tiled X is all the sweeps read
         ctx.refresh_tables(theta_vb, zeta_vb, c_next=c)  # :61-63
         sig2_beta_for_m2 = sig2_beta_vb  # m2_beta always pairs gam/mu with the sig2_beta_vb of their sweep (:113,:235)
 
@@ -410,10 +424,21 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
             sig2_beta_for_m2 = sig2_beta_vb
             _lap("sweep")
             colsum_m2 = m2_of(sums)  # :235
-            rows = ctx.rowsums_zpart()
-            _lap("rowsums")
-            glob = comm.allreduce_sum(np.concatenate([rows, [sums["colsum_gam"].sum(), np.dot(tau_vb, colsum_m2)]]))
-            rowsum_zpart, sum_gam, tau_dot_m2 = glob[:p], float(glob[p]), float(glob[p + 1])
+            local = [sums["colsum_gam"].sum(), np.dot(tau_vb, colsum_m2)]
+            if (comm.world_size > 1 and callable(getattr(comm, "allreduce_sum_device", None))
+                    and hasattr(ctx, "rowsums_zpart_dev")):
+                # the row sums never visit the host before the all-reduce: NCCL reduces the library's device buffer in
+                # place (aq_rowsums_zpart_dev), the two scalars ride in a second, tiny message
+                ptr = ctx.rowsums_zpart_dev()
+                _lap("rowsums")
+                rowsum_zpart = comm.allreduce_sum_device(ptr, p)
+                glob = comm.allreduce_sum(np.array(local))
+                sum_gam, tau_dot_m2 = float(glob[0]), float(glob[1])
+            else:
+                rows = ctx.rowsums_zpart()
+                _lap("rowsums")
+                glob = comm.allreduce_sum(np.concatenate([rows, local]))
+                rowsum_zpart, sum_gam, tau_dot_m2 = glob[:p], float(glob[p]), float(glob[p + 1])
             _lap("allreduce")
 
             sqrt_c = 1.0 if abs(c - 1) < ALL_EQUAL_TOL else math.sqrt(c)  # R/update_vb.R:219-229

@@ -678,9 +678,20 @@ int aq_create_prepared(aq_ctx** out, const aq_prep* prep, int q_local, const dou
 
 int aq_get_x(aq_ctx* c, double* X) {
     if (!c || !X) return fail(AQ_EINVAL, "aq_get_x: NULL argument");
+    if (!c->xraw) return fail(AQ_ESTATE, "aq_get_x after aq_release_x");
     AQ_CUDA(cudaSetDevice(c->device));
     AQ_CUDA(cudaMemcpyAsync(X, c->xraw, sizeof(double) * (size_t)c->n * c->p, cudaMemcpyDeviceToHost, c->stream));
     AQ_CUDA(cudaStreamSynchronize(c->stream));
+    return AQ_OK;
+}
+
+int aq_release_x(aq_ctx* c) {
+    if (!c) return fail(AQ_EINVAL, "NULL context");
+    if (c->has_mis) return fail(AQ_ESTATE, "aq_release_x: the missing-response kernel reads the untiled X");
+    AQ_CUDA(cudaSetDevice(c->device));
+    AQ_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->xraw) AQ_CUDA(cudaFree(c->xraw));
+    c->xraw = nullptr;
     return AQ_OK;
 }
 
@@ -911,6 +922,7 @@ int aq_set_order(aq_ctx* c, const int32_t* shuffled_ind) {
         for (int j = 0; j < c->p; ++j) ord[j] = j;
     }
     if (ord == c->order) return AQ_OK;
+    if (!c->xraw) return fail(AQ_ESTATE, "aq_set_order: a new order needs the untiled X, which aq_release_x freed");
     c->order.swap(ord);
     int rc = retile(c);
     if (rc != AQ_OK) return rc;
@@ -1146,6 +1158,7 @@ int fetch_mis(aq_ctx* c, const int* rows, double* const* outs, int nout) {
 int aq_set_missing(aq_ctx* c, const double* mis_pat, double* n_obs) {
     if (!c || !mis_pat) return fail(AQ_EINVAL, "aq_set_missing: NULL argument");
     if (c->n > 2048) return fail(AQ_EUNSUPPORTED, "aq_set_missing: the missing-response kernel covers n <= 2048");
+    if (!c->xraw) return fail(AQ_ESTATE, "aq_set_missing after aq_release_x");
     AQ_CUDA(cudaSetDevice(c->device));
     const size_t pq = (size_t)c->p_pad * c->q_pad;
     if (!c->mask) AQ_CUDA(cudaMalloc((void**)&c->mask, sizeof(unsigned long long) * 32 * (size_t)c->q_pad));

@@ -44,6 +44,10 @@ class SweepContext:
         _lib.check(self._lib.aq_get_x(self._ctx, _lib.dptr(X)))
         return X
 
+    def release_x(self):
+        """Free the untiled device copy of X (aq_release_x): fixed sweep order, no missing responses from here on."""
+        _lib.check(self._lib.aq_release_x(self._ctx))
+
     def get_y(self):
         Y = np.empty((self.n, self.q), order="F")
         _lib.check(self._lib.aq_get_y(self._ctx, _lib.dptr(Y)))

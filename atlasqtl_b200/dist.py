@@ -15,6 +15,14 @@ def slab_bounds(q, rank, world_size):
     return k0, k0 + base + (1 if rank < rem else 0)
 
 
+class _DeviceArray:
+    """A raw device pointer dressed as a CUDA array (float64, 1-D) so that torch can alias it without a copy."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f8", "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+
+
 class TorchComm:
     """allreduce_sum over the default process group.  NCCL needs device tensors: the (small) buffer goes
     host -> device -> all-reduce -> host; `gloo` (CPU tests) reduces the host tensor directly."""
@@ -29,11 +37,23 @@ class TorchComm:
         self.backend = dist.get_backend()
         self.device = device if device is not None else (
             torch.device("cuda", torch.cuda.current_device()) if self.backend == "nccl" else torch.device("cpu"))
+        if self.device.type != "cuda":
+            self.allreduce_sum_device = None   # (the core checks for a callable: host buffers go through allreduce_sum)
 
     def allreduce_sum(self, x):
         t = self._torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))
         if self.device.type == "cuda":
             t = t.to(self.device, non_blocking=False)
+        self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    def allreduce_sum_device(self, dev_ptr, count):
+        """In-place NCCL all-reduce of `count` doubles at device address `dev_ptr` (a buffer owned by the CUDA library,
+        e.g. aq_rowsums_zpart_dev), then one download.  Only with the nccl backend (AttributeError otherwise, which the
+        core treats as "not available")."""
+        if self.device.type != "cuda":
+            raise AttributeError("allreduce_sum_device needs the nccl backend")
+        t = self._torch.as_tensor(_DeviceArray(dev_ptr, count), device=self.device)
         self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM)
         return t.cpu().numpy()
 

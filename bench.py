@@ -30,11 +30,31 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the main sweep kernel, from the committed
-# `ncu --set full` capture of this very command (profiles/r1_ncu_sweep_c2_full_v7.txt, tools/profile_c2.sh): 43.77 GB +
-# 15.75 GB for 1184 of the 1250 trait tiles; the algorithmic figure is 56 B per update (read gam, mu, D, W, I0; write gam,
-# mu) = 53 GB for them, + 0.5 GB of per-tile row-sum partials.
-NCU_TRAFFIC_BYTES = {("C2", 1): 59.53e9}
+# roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the sweep kernel, taken from the ncu
+# `--set full` capture recorded in profiles/ncu_traffic.json by tools/profile_c2.sh.  The record carries the hash of the
+# kernel sources it was captured from; it is reported only while that hash matches the sources of the library being
+# benchmarked -- otherwise the field is null and `traffic_source` says which capture is stale.  Never a constant.
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+
+
+def kernel_source_hash():
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "atlasqtl_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(config, world):
+    try:
+        rec = json.load(open(TRAFFIC_FILE))[config][str(world)]
+    except (OSError, KeyError, ValueError):
+        return None, "no ncu capture recorded for this config / GPU count (profiles/ncu_traffic.json)"
+    if rec.get("src_hash") != kernel_source_hash():
+        return None, f"stale: {rec.get('source')} was captured from other kernel sources ({rec.get('src_hash')})"
+    return rec["bytes"], rec.get("source")
 
 FP64_PEAK_TFLOPS = 37.05  # measured DMMA m8n8k4 peak on this pool's B200 (profiles/r1_fp64_peaks_microbench.txt);
                           # MEASURED_PEAKS.json has no fp64 entry (bf16 / HBM only)
@@ -45,38 +65,63 @@ def log(*a):
 
 
 # ----------------------------------------------------------------------------- workload
-def make_workload(name, k_first, k_last, seed=123, threads=None):
-    """Synthetic data + default hyper / init of BASELINE config `name` for the trait slab [k_first, k_last)."""
+PACKED_ABOVE_BYTES = 4 << 30   # X larger than this is generated as packed 2-bit calls and standardised on the device
+
+
+def make_workload(name, k_first, k_last, seed=123, threads=None, force_dense=False):
+    """Synthetic data + default hyper / init of BASELINE config `name` for the trait slab [k_first, k_last).
+
+    Returns (cfg, X, Y, hyper, init).  X is the standardised n x p matrix (Fortran) -- or, when it would exceed
+    PACKED_ABOVE_BYTES (C3: 4.8 GB, C5: 20 GB per rank), a dict(packed=uint8 [p][ceil(n/4)], n=n) of 2-bit genotype calls
+    that the library standardises on the device (aq_prep_geno, R/prepare_atlasqtl.R:57), with Y then RAW (centred there)."""
     from concurrent.futures import ThreadPoolExecutor
 
     from scipy import special as sp
 
     from atlasqtl_b200 import hyper_init, synthetic
+    from atlasqtl_b200.device import pack_genotypes
     cfg = dict(synthetic.CONFIGS[name])
     n, p, q = cfg["n"], cfg["p"], cfg["q"]
+    threads = threads or host_threads()
+    packed = (not force_dense) and 8.0 * n * p > PACKED_ABOVE_BYTES
     rng = np.random.default_rng(seed)
-    # genotypes, standardised (constant columns are re-drawn rather than dropped so that p stays as named)
-    X = np.empty((n, p), order="F")
-    maf = 0.25
-    for j0 in range(0, p, 8192):
-        j1 = min(p, j0 + 8192)
-        G = rng.binomial(2, maf, size=(n, j1 - j0)).astype(np.float64)
-        sd = G.std(axis=0, ddof=1)
-        bad = sd == 0
-        if bad.any():
-            G[: 2, bad] = [[0.0], [1.0]]
-            sd = G.std(axis=0, ddof=1)
-        X[:, j0:j1] = (G - G.mean(axis=0)) / sd
     p_act = cfg.get("p_act", cfg.get("hotspots", 20))
     q_act = cfg.get("q_act", q)
-    act = rng.choice(p, size=p_act, replace=False)
+    act = np.sort(rng.choice(p, size=p_act, replace=False))
     traits_act = rng.choice(q, size=q_act, replace=False)
     beta = np.zeros((p_act, q))
     pat = rng.random((p_act, q_act)) < 0.2
     beta[:, traits_act] = pat * rng.normal(0.0, cfg.get("beta_sd", 1.0), size=(p_act, q_act))
+    maf = 0.25
+    chunk_cols = 8192
+    starts = list(range(0, p, chunk_cols))
+    X = None if packed else np.empty((n, p), order="F")
+    G_packed = np.empty((p, (n + 3) // 4), dtype=np.uint8) if packed else None
+    X_act = np.empty((n, p_act))
+
+    def gen(j0):   # genotypes of one column chunk (its own generator stream: the same data whatever the thread count)
+        j1 = min(p, j0 + chunk_cols)
+        G = np.random.default_rng([seed, 11, j0]).binomial(2, maf, size=(n, j1 - j0)).astype(np.float64)
+        sd = G.std(axis=0, ddof=1)
+        bad = sd == 0   # constant columns are re-drawn rather than dropped so that p stays as named
+        if bad.any():
+            G[:2, bad] = [[0.0], [1.0]]
+            sd = G.std(axis=0, ddof=1)
+        Z = (G - G.mean(axis=0)) / sd
+        if packed:
+            G_packed[j0:j1] = pack_genotypes(G)
+        else:
+            X[:, j0:j1] = Z
+        lo, hi = np.searchsorted(act, [j0, j1])
+        X_act[:, lo:hi] = Z[:, act[lo:hi] - j0]
+
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(gen, starts))
     ql = k_last - k_first
-    Y = X[:, act] @ beta[:, k_first:k_last] + np.random.default_rng(seed + 1 + k_first).normal(size=(n, ql))
-    Y = np.asfortranarray(Y - Y.mean(axis=0))
+    Y = X_act @ beta[:, k_first:k_last] + np.random.default_rng(seed + 1 + k_first).normal(size=(n, ql))
+    if not packed:
+        Y = Y - Y.mean(axis=0)   # (packed path: centred on the device, like scale(Y, scale = FALSE) R/prepare_atlasqtl.R:83)
+    Y = np.asfortranarray(Y)
     e_p = max(1.0, float(pat.sum(axis=0).mean()))
     p0 = (e_p, max(10.0, 2.0 * e_p))  # (mean, variance) of the prior number of active SNPs per trait
     t02 = hyper_init._solve_t02(p, p0)
@@ -87,7 +132,7 @@ def make_workload(name, k_first, k_last, seed=123, threads=None):
     gam = np.empty((p, ql), order="F")
     mu = np.empty((p, ql), order="F")
     sd0 = 1e-4 + t02
-    chunk = 256
+    chunk = max(1, min(256, (64 << 20) // (4 * p)))
 
     def fill(k0):
         r = np.random.default_rng([seed, 7, k_first + k0])
@@ -96,7 +141,7 @@ def make_workload(name, k_first, k_last, seed=123, threads=None):
         gam[:, k0:k1] = sp.ndtr(n0 + sd0 * z).T
         mu[:, k0:k1] = r.standard_normal((k1 - k0, p), dtype=np.float32).T
 
-    with ThreadPoolExecutor(threads or min(32, os.cpu_count() or 1)) as ex:
+    with ThreadPoolExecutor(threads) as ex:
         list(ex.map(fill, range(0, ql, chunk)))
     r = np.random.default_rng(seed + 3)
     sig02_inv = float(r.gamma(shape=max(p, q), scale=1.0))
@@ -105,7 +150,12 @@ def make_workload(name, k_first, k_last, seed=123, threads=None):
                 sig2_theta_vb=1 / (q + r.gamma(shape=sig02_inv * q, scale=1.0, size=p)),
                 tau_vb=np.full(q, tau0), theta_vb=r.normal(0.0, 1 / np.sqrt(sig02_inv * q), size=p),
                 zeta_vb=r.normal(n0, np.sqrt(t02), size=q))
-    return cfg, X, Y, hyper, init
+    return cfg, (dict(packed=G_packed, n=n) if packed else X), Y, hyper, init
+
+
+def host_threads():
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    return max(1, min(32, ncpu // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -152,11 +202,11 @@ def reference_sample(cfg, X, Y, hyper, init, p_s=8192, traits_per_thread=1, thre
 
     from oracle import native
     threads = threads or (os.cpu_count() or 1)
-    n, p = X.shape
+    n, p = cfg["n"], cfg["p"]
     p_s = min(p, p_s)
     q_s = min(Y.shape[1], threads * traits_per_thread)
-    Xs = np.asfortranarray(X[:, :p_s])
-    Ys = np.asfortranarray(Y[:, :q_s])
+    Xs = dense_columns(X, 0, p_s)
+    Ys = np.asfortranarray(Y[:, :q_s] - Y[:, :q_s].mean(axis=0))
     kind = "reference" if native.ref_available() else "port"
     impl = "reference" if kind == "reference" else "oracle"
     t0 = time.time()
@@ -197,12 +247,24 @@ def reference_sample(cfg, X, Y, hyper, init, p_s=8192, traits_per_thread=1, thre
                 value_at_full_p_est=value * p_s / p)
 
 
+def dense_columns(X, j0, j1):
+    """Standardised columns [j0, j1) of the workload's X as a dense Fortran matrix (unpacks 2-bit calls if need be)."""
+    if not isinstance(X, dict):
+        return np.asfortranarray(X[:, j0:j1])
+    g = X["packed"][j0:j1]
+    n = X["n"]
+    G = np.stack([(g >> s) & 3 for s in (0, 2, 4, 6)], axis=2).reshape(g.shape[0], -1)[:, :n].T.astype(np.float64)
+    return np.asfortranarray((G - G.mean(axis=0)) / G.std(axis=0, ddof=1))
+
+
 def port_sample(X, Y, init, threads=None, target_s=6.0):
     """Best-effort CPU (ours, primal form, all host threads) on a q-slice of the full-n, full-p workload."""
     from scipy import special as sp
 
     from oracle import native
     threads = threads or (os.cpu_count() or 1)
+    if isinstance(X, dict):
+        raise ValueError("port_sample needs the dense X")
     n, p = X.shape
     q_s = min(Y.shape[1], max(threads, int(target_s * threads * 1.5e9 / (4.0 * n * p))))
     Ys = np.asfortranarray(Y[:, :q_s])
@@ -262,8 +324,12 @@ def main():
             return
         from oracle import native
         native.build()
-        ws = make_workload(args.config, 0, min(q, 4 * (os.cpu_count() or 1)))
+        ncpu = os.cpu_count() or 1
+        ws = make_workload(args.config, 0, min(q, 4 * ncpu))
         res = reference_sample(*ws, steps=K, warmup=W)
+        # the reference's dual form needs the p x p Gram matrix (20 GB at C2) and O(p) work per update: it is timed on a
+        # bounded SAMPLE of the workload, and the line says so where the config is named
+        config["workload"] += f" -- REFERENCE ARM TIMES A SAMPLE: {res['sample']}"
         line = {"impl": "reference", "metric": "SNPxtrait CAVI updates/s", "value": res["value"],
                 "unit": "updates/s", "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": res["ms_per_step"],
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -275,7 +341,7 @@ def main():
 
     import torch
     from atlasqtl_b200 import core
-    from atlasqtl_b200.device import SweepContext
+    from atlasqtl_b200.device import PreparedPredictors, SweepContext
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the hot path")
     torch.cuda.set_device(local_rank)
@@ -292,9 +358,18 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         comm = TorchComm()
     k0, k1 = slab_bounds(q, rank, world)
+    ql = k1 - k0
+    # memory plan of this rank (bytes): five p x q_local arrays + X (tiled; the untiled copy is released) -- refuse early
+    # rather than drive the GPU out of memory
+    need = 5 * 8.0 * p * ql + 1.15 * 8.0 * n * p * 2 + 16.0 * n * ql
+    free_b, total_b = torch.cuda.mem_get_info()
+    if need > 0.97 * free_b:
+        raise SystemExit(f"{args.config} on {world} GPU(s) needs ~{need / 2**30:.0f} GiB per GPU, {free_b / 2**30:.0f} GiB free: "
+                         "use more GPUs (the traits are sharded, X is replicated)")
     t_setup = time.time()
     cfg, X, Y, hyper, init = make_workload(args.config, k0, k1)
-    log(f"[rank {rank}] workload built in {time.time() - t_setup:.1f} s (slab {k0}:{k1})")
+    log(f"[rank {rank}] workload built in {time.time() - t_setup:.1f} s (slab {k0}:{k1}, "
+        f"X {'packed 2-bit calls' if isinstance(X, dict) else 'dense'})")
 
     def barrier_sync():
         torch.cuda.synchronize()
@@ -321,31 +396,52 @@ def main():
 
     trace = []
     t_up = time.time()
-    ctx = SweepContext(X, Y, device=local_rank)
+    if isinstance(X, dict):
+        prep = PreparedPredictors(packed=X["packed"], n=X["n"], device=local_rank)
+        if prep.p != p:
+            raise SystemExit(f"device pre-processing kept {prep.p} of {p} SNPs (duplicates in the synthetic genotypes)")
+        ctx = SweepContext.from_prepared(prep, Y)
+        prep.close()
+        Xarg = prep   # the core only asks for .shape
+        if world > 1:
+            X["packed"] = None   # (kept at N = 1 for the CPU baseline's sample)
+    else:
+        ctx = SweepContext(X, Y, device=local_rank)
+        Xarg = X
     log(f"[rank {rank}] context created in {time.time() - t_up:.1f} s")
     try:
-        core.atlasqtl_global_local_core_(Y, X, q, anneal, 1, 1e-300, W + K, 0, hyper, init, debug=False, comm=comm,
-                                         slab=(k0, k1), ctx=ctx, trace=trace, iter_hook=hook)
+        core.atlasqtl_global_local_core_(Y, Xarg, q, anneal, 1, 1e-300, W + K, 0, hyper, init, debug=False, comm=comm,
+                                         slab=(k0, k1), ctx=ctx, trace=trace, iter_hook=hook, release_x=True)
         clocks = sampler.stop() if rank == 0 else None
         timed = [r for r in trace if W < r["it"] <= W + K]
-        if rank == 0 and timed and "host_ms" in timed[0]:
-            keys = list(timed[0]["host_ms"])
-            log("[host wall-clock per step, ms] " + ", ".join(
-                f"{k}={np.mean([r['host_ms'].get(k, 0.0) for r in timed]):.2f}" for k in keys))
+        seg_keys = list(timed[0].get("host_ms", {})) if timed else []
+        host_ms = np.array([np.mean([r["host_ms"].get(k, 0.0) for r in timed]) for k in seg_keys])
         dev_ms = sum(r["sweep_ms"] + r["rows_ms"] + r["tables_ms"] for r in timed)
-        sweep_ms = float(np.mean([r["sweep_ms"] for r in timed]))
+        per = np.array([np.mean([r[k] for r in timed]) for k in ("sweep_ms", "rows_ms", "tables_ms")])
         wall_ms = 1e3 * (marks["t1"] - marks["t0"])
-        red = np.array([dev_ms, wall_ms, sweep_ms])
+        red = np.concatenate([[dev_ms, wall_ms], per, host_ms])
         if world > 1:
             t = torch.tensor(red, device="cuda")
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
             red = t.cpu().numpy()
-        dev_ms, wall_ms, sweep_ms_max = (float(v) for v in red)
-        ql = k1 - k0
+        dev_ms, wall_ms = float(red[0]), float(red[1])
+        sweep_ms, rows_ms, tables_ms = (float(v) for v in red[2:5])
+        host_ms = red[5:]
+        if rank == 0 and seg_keys:
+            log("[host wall-clock per step, ms, max over ranks] " + ", ".join(f"{k}={v:.2f}" for k, v in zip(seg_keys, host_ms)))
         dims = ctx.dims()
-        h2d = 8 * (3 * ql + p + ql) + (8 * (p + 2) if world > 1 else 0)
-        d2h = 8 * (5 * dims["q_pad"] + p + 1) + (8 * (p + 2) if world > 1 else 0)
+        plan = ctx.sweep_plan()
+        dev_reduce = world > 1 and callable(getattr(comm, "allreduce_sum_device", None))
+        # per step: H2D tau / log_tau / sig2_beta (q_local each), theta (p), zeta (q_local) [+ the all-reduce message];
+        # D2H the five column-sum vectors, the row sums (p), the ELBO scalar [+ the all-reduce result]
+        h2d = 8 * (3 * ql + p + ql) + (8 * 2 if dev_reduce else (8 * (p + 2) if world > 1 else 0))
+        d2h = 8 * (5 * dims["q_pad"] + p + 1) + (8 * 2 if dev_reduce else (8 * (p + 2) if world > 1 else 0))
         n_launch = launches["t1"] - launches["t0"]
+        lbs = [r["lb"] for r in trace if r["lb"] is not None]
+        check = {"lb_last": lbs[-1] if lbs else None, "lb_it": max((r["it"] for r in trace if r["lb"] is not None), default=None),
+                 "sum_gam": trace[-1]["sum_gam"], "it": trace[-1]["it"],
+                 "note": "global quantities after the last step (all-reduced over ranks): lines of the same config at "
+                         "different GPU counts must agree to ~1e-10 relative"}
     finally:
         ctx.close()
     if rank != 0:
@@ -354,6 +450,7 @@ def main():
         return
     flops_per_sweep = 4.0 * n * p * ql  # algorithmic: 2n (X_j'r) + 2n (rank-1 update) per SNP x trait, this rank
     achieved = flops_per_sweep / (sweep_ms * 1e-3) / 1e12
+    traffic, traffic_src = ncu_traffic(args.config, world)
     line = {"metric": "SNPxtrait CAVI updates/s", "value": p * q * K / (dev_ms * 1e-3), "unit": "updates/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
@@ -362,15 +459,18 @@ def main():
             "gpu_launches": int(n_launch),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                          "frac": achieved / FP64_PEAK_TFLOPS,
-                         "traffic": NCU_TRAFFIC_BYTES.get((args.config, world)),
-                         "kernel": "sweep_kernel (fp64 DMMA m8n8k4): full-size tile launch + 8-trait tail launch of one sweep",
-                         "ms": sweep_ms,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "traffic_algorithmic": 56.0 * p * ql + 8.0 * n * p + 16.0 * n * ql,
+                         "kernel": "sweep_kernel (fp64 DMMA m8n8k4), one sweep of this rank's trait slab",
+                         "ms": sweep_ms, "plan": plan,
                          "peak_source": "measured fp64 DMMA peak, tools/microbench/fp64_peaks.cu on this pool "
                                         "(MEASURED_PEAKS.json has no fp64 entry)",
-                         "algorithmic": "4*n flops per SNPxtrait update"},
-            "clocks": clocks,
-            "per_step_ms": {"sweep": sweep_ms, "rowsums": float(np.mean([r["rows_ms"] for r in timed])),
-                            "tables": float(np.mean([r["tables_ms"] for r in timed]))}}
+                         "algorithmic": "4*n flops per SNPxtrait update; HBM: 56 B per update (read gam, mu, D, W, I0; write "
+                                        "gam, mu: one table more than the reference's 48 B, W / I0 replace its two log-CDF "
+                                        "tables plus the Z pass) + X once + residual in / out"},
+            "clocks": clocks, "check": check,
+            "per_step_ms": {"sweep": sweep_ms, "rowsums": rows_ms, "tables": tables_ms,
+                            "host": {k: float(v) for k, v in zip(seg_keys, host_ms)}, "over_ranks": "max"}}
     if world == 1 and not args.no_cpu_baseline:
         try:
             from oracle import native
@@ -378,7 +478,8 @@ def main():
             ref = reference_sample(cfg, X, Y, hyper, init, steps=2, warmup=1)
             line["cpu_baseline"] = {k: ref[k] for k in ("value", "unit", "cores", "kind", "sample")}
             line["cpu_baseline"]["value_at_full_p_est"] = ref["value_at_full_p_est"]
-            line["cpu_port"] = port_sample(X, Y, init)
+            if not isinstance(X, dict):
+                line["cpu_port"] = port_sample(X, Y, init)
         except Exception as e:  # the baseline is a report, never the product path
             line["cpu_baseline"] = {"error": repr(e)}
     emit(line)

@@ -94,6 +94,13 @@ int64_t aq_prep_launch_count(const aq_prep* prep);
 int aq_create_prepared(aq_ctx** out, const aq_prep* prep, int q_local, const double* Y_raw, double* n_obs);
 int aq_get_x(aq_ctx* ctx, double* X);
 int aq_get_y(aq_ctx* ctx, double* Y);
+/*
+ * Free the context's untiled copy of X ([p][n] doubles: 20 GB at n = 5000, p = 500k).  The sweep reads the tiled images
+ * only; the untiled copy serves re-tiling for a new shuffled_ind (aq_set_order), the missing-response kernel and aq_get_x,
+ * which return AQ_ESTATE afterwards.  For runs with the reference's fixed identity order (R/atlasqtl_global_local_core.R:162)
+ * and no missing responses X is then held once.
+ */
+int aq_release_x(aq_ctx* ctx);
 
 /* Dimensions and padded leading dimensions of the device layout (for callers that pass _dev pointers). */
 int aq_dims(const aq_ctx* ctx, int* n, int* p, int* q_local, int* p_pad, int* q_pad);
