@@ -50,4 +50,7 @@ CONFIGS = {  # BASELINE.json configs[0..4]
     "C3": dict(n=3000, p=200000, q=1500, p_act=500, q_act=750, anneal=(1, 2, 10)),
     "C4": dict(n=500, p=10000, q=5000, hotspots=20, beta_sd=0.5, anneal=(1, 2, 10)),
     "C5": dict(n=5000, p=500000, q=20000, p_act=1000, q_act=10000, anneal=(1, 2, 10)),
+    # not a BASELINE config: what ONE GPU of the 8 sees of C5 (its 2500-trait slab), on a 32nd of the SNPs -- a one-GPU
+    # rehearsal of the C5 code path (packed genotypes, 8-CTA sample-split clusters) for development and profiling
+    "C5slab": dict(n=5000, p=16000, q=2500, p_act=100, q_act=1250, anneal=(1, 2, 10)),
 }

@@ -65,7 +65,8 @@ def log(*a):
 
 
 # ----------------------------------------------------------------------------- workload
-PACKED_ABOVE_BYTES = 4 << 30   # X larger than this is generated as packed 2-bit calls and standardised on the device
+# X larger than this is generated as packed 2-bit calls and standardised on the device
+PACKED_ABOVE_BYTES = int(float(os.environ.get("AQ_BENCH_PACKED_ABOVE_GB", "4")) * (1 << 30))
 
 
 def make_workload(name, k_first, k_last, seed=123, threads=None, force_dense=False):
@@ -366,6 +367,17 @@ def main():
     if need > 0.97 * free_b:
         raise SystemExit(f"{args.config} on {world} GPU(s) needs ~{need / 2**30:.0f} GiB per GPU, {free_b / 2**30:.0f} GiB free: "
                          "use more GPUs (the traits are sharded, X is replicated)")
+    # ... and the host: every rank builds its slab's initial state (two p x q_local matrices) and X in host memory
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+        host_need = (2 * 8.0 * p * ql * 1.3 + min(8.0 * n * p, PACKED_ABOVE_BYTES) + 0.3 * n * p) * local_world
+        if host_need > 0.85 * avail:
+            raise SystemExit(f"{args.config} on {world} GPU(s) needs ~{host_need / 2**30:.0f} GiB of host memory to build the "
+                             f"synthetic state, {avail / 2**30:.0f} GiB available")
+    except ImportError:
+        pass
     t_setup = time.time()
     cfg, X, Y, hyper, init = make_workload(args.config, k0, k1)
     log(f"[rank {rank}] workload built in {time.time() - t_setup:.1f} s (slab {k0}:{k1}, "

@@ -33,8 +33,10 @@ def _run_and_compare(name, live_reference=False):
     gold = np.load(path)
     X, Y, hyper, init, anneal = mt.problem(name)
     p, q = X.shape[1], Y.shape[1]
-    # same inputs as the golden run? (NumPy generator streams and brentq are deterministic; this tells drift from a bug)
-    np.testing.assert_allclose(mt.input_checksums(X, Y, hyper, init), gold["in_check"], rtol=1e-12)
+    # same inputs as the golden run?  NumPy generator streams and brentq are deterministic; Y = G beta + noise goes through
+    # the host BLAS, whose summation order differs between CPUs in the last bit (and sums of centred data are ~0): the
+    # check tells "inputs drifted" (another recipe / seed / library version) from "results differ"
+    np.testing.assert_allclose(mt.input_checksums(X, Y, hyper, init), gold["in_check"], rtol=1e-9, atol=1e-7)
     trace = []
     with SweepContext(X, Y) as ctx:
         out = core.atlasqtl_global_local_core_(Y, X, q, anneal, 1, float(gold["tol"]), 1000, 0, hyper, init, debug=True,

@@ -252,11 +252,11 @@ def test_bfdr_device_ties_at_the_boundary():
 
 @pytest.mark.parametrize("margin", [1e-9, -1e-9, 1e-12, -1e-12])
 def test_bfdr_device_near_threshold_boundary(margin):
-    """Adversarial: the running mean of 1 - PPI reaches thres -+ margin exactly at one element.  The reference decides with
-    a sequential cumsum / rank < thres (R/summarise_output.R:216-218); the device path with fixed-order tree sums of the same
-    terms.  The two can only disagree when |mean - thres| is at the rounding level of a sum of N terms (~N * 1e-16 * thres);
-    down to a relative margin of 1e-12 (N = 4800 here) the sets must be identical.  Checked against an exactly rounded
-    evaluation (math.fsum) and the oracle's assign_bFDR."""
+    """Adversarial: thres is placed at (1 +- margin) x the running mean of 1 - PPI at one rank, so that the decision
+    `cumsum(1 - ppi) / rank < thres` (R/summarise_output.R:216-218) of that element hangs on a relative 1e-9 / 1e-12.
+    The reference decides with a sequential cumsum, the device path with fixed-order tree sums of the same terms: they can
+    only disagree when |mean - thres| is at the rounding level of a sum of N terms (N = 2800 here: <= 3e-13 relative).
+    Checked against an exactly rounded evaluation (math.fsum) and the ORACLE's assign_bFDR."""
     import math
 
     from atlasqtl_b200 import summarise
@@ -264,31 +264,22 @@ def test_bfdr_device_near_threshold_boundary(margin):
     from oracle import vb_oracle
     rng = np.random.default_rng(21)
     n, p, q = 30, 120, 40
-    thres = 0.05
     X = np.asfortranarray(rng.normal(size=(n, p)))
     Y = np.asfortranarray(rng.normal(size=(n, q)))
-    e = np.sort(rng.uniform(size=p * q) ** 3)   # 1 - PPI, ascending = decreasing PPI; distinct with probability 1
-    # find the prefix whose mean is closest below thres, then move its LAST element so that the mean lands at thres (1 + margin)
-    cs = np.cumsum(e) / np.arange(1, e.size + 1)
-    m = int(np.searchsorted(cs, thres))          # cs[m - 1] < thres <= cs[m]
-    assert 50 < m < e.size - 50
-    target = thres * (1 + margin) * (m + 1) - math.fsum(e[:m])
-    assert e[m - 1] < target < e[m + 1]
-    e[m] = target
-    assert np.all(np.diff(e) > 0)
-    gam = np.asfortranarray((1 - e)[rng.permutation(e.size)].reshape(p, q))
-    ee = np.sort(1 - gam.flatten())              # what the device actually sees (1 - (1 - e) is not e in general)
-    exact_mean = lambda k: math.fsum(ee[:k]) / k
-    k_sel = 0
-    while k_sel < ee.size and exact_mean(k_sel + 1) < thres:
-        k_sel += 1
-    if abs(exact_mean(m + 1) / thres - 1) < 1e-14:
-        pytest.skip("rounding of 1 - gam moved the constructed mean onto the threshold itself")
+    gam = np.asfortranarray(1 - rng.uniform(size=(p, q)) ** 3)   # distinct with probability 1
+    ee = np.sort(1 - gam.flatten())                                # what both sides see: e = 1 - gam_vb, ascending
+    assert np.all(np.diff(ee) > 0)
+    m = 2800
+    mean_m1 = math.fsum(ee[:m + 1]) / (m + 1)
+    thres = mean_m1 * (1 + margin)       # margin > 0: element m is the last one selected; margin < 0: the first one left out
+    k_sel = m + 1 if margin > 0 else m
+    exact_ok = lambda k: math.fsum(ee[:k]) / k < thres
+    assert exact_ok(k_sel) and not exact_ok(k_sel + 1)
     with SweepContext(X, Y) as ctx:
         ctx.set_state(gam, np.zeros((p, q)))
         rows, cols, nsel = summarise.select_bFDR_device(ctx, thres)
     want = vb_oracle.assign_bFDR(gam) < thres
-    assert want.sum() == k_sel == (m + 1 if margin < 0 else m)
+    assert want.sum() == k_sel
     got = np.zeros_like(want)
     got[rows, cols] = True
     assert nsel == k_sel

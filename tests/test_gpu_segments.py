@@ -45,14 +45,15 @@ def test_segmented_sweep_matches_oracle_and_unsegmented(oracle_built, monkeypatc
     one = _sweep(monkeypatch, X, Y, si, order, {"AQ_NO_SEG": "1", "AQ_NO_TAIL": "1"})
     assert seg["plan"]["nseg"] == nseg and one["plan"]["nseg"] == 1
     assert seg["plan"]["ntiles"] > seg["plan"]["groups"]
-    # segmented == unsegmented: the per-pair arithmetic is identical, only the column sums are added in segment order
-    assert np.array_equal(seg["st"]["gam_vb"], one["st"]["gam_vb"])
-    assert np.array_equal(seg["st"]["mu_beta_vb"], one["st"]["mu_beta_vb"])
-    assert np.array_equal(seg["R"], one["R"])
-    for key in ("colsum_gam", "colsum_gam_mu2", "colsum_beta2", "colsum_zpart"):
-        np.testing.assert_allclose(seg["out2"][key], one["out2"][key], rtol=1e-13, atol=1e-13)
-    assert np.array_equal(seg["out2"]["resid_sq"], one["out2"]["resid_sq"])
-    np.testing.assert_allclose(seg["rows"], one["rows"], rtol=1e-13, atol=1e-13)
+    # segmented vs unsegmented, two sweeps each: the same mathematics, but not bit for bit -- the first block of a segment
+    # forms S from the fully updated residual, where the unsegmented sweep corrects a look-ahead S by the cross Gram block
+    # (S_{b+1} = X_{b+1}' R_{b-1} - G_{b+1,b} Delta_b), and the column sums are added in segment order
+    assert np.abs(seg["st"]["gam_vb"] - one["st"]["gam_vb"]).max() <= 1e-12
+    assert np.abs(seg["st"]["mu_beta_vb"] - one["st"]["mu_beta_vb"]).max() <= 1e-12 * max(1.0, np.abs(one["st"]["mu_beta_vb"]).max())
+    np.testing.assert_allclose(seg["R"], one["R"], atol=1e-11)
+    for key in ("colsum_gam", "colsum_gam_mu2", "colsum_beta2", "colsum_zpart", "resid_sq"):
+        np.testing.assert_allclose(seg["out2"][key], one["out2"][key], rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(seg["rows"], one["rows"], rtol=1e-11, atol=1e-11)
     # the state set-up (mode 1 of the kernel) is segmented as well
     for key in ("colsum_gam", "colsum_gam_mu2", "colsum_beta2", "resid_sq"):
         np.testing.assert_allclose(seg["st0"][key], one["st0"][key], rtol=1e-13, atol=1e-13)
