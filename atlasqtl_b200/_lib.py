@@ -5,7 +5,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libatlasqtl_b200.so")
+# (AQ_LIB: development knob to load another build of the same library, e.g. for A/B timing of a kernel variant)
+LIB_PATH = os.environ.get("AQ_LIB") or os.path.join(_HERE, "libatlasqtl_b200.so")
 _DP = ctypes.POINTER(ctypes.c_double)
 _IP = ctypes.POINTER(ctypes.c_int32)
 

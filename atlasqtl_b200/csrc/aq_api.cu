@@ -74,11 +74,18 @@ bool pick_nt(int nt, bool cl, int ncta, CfgInfo* out) {
 }
 
 bool pick_cfg(int n, CfgInfo* out) {
-    // development knob: AQ_FORCE_CLUSTER=2|4|8 selects the sample-split cluster kernel even where one CTA suffices
+    // development knob: AQ_FORCE_CLUSTER=2..8 selects the sample-split cluster kernel with that many CTAs per cluster
+    // (even where one CTA suffices); by default the smallest power of two that holds the samples
     const char* fc = std::getenv("AQ_FORCE_CLUSTER");
     int ncta = fc ? std::atoi(fc) : 0;
-    if (ncta != 2 && ncta != 4 && ncta != 8) ncta = 1;
+    const bool forced = ncta >= 2 && ncta <= kMaxCluster;
+    if (!forced) ncta = 1;
+    // 2688 < n <= 3360 (C3: n = 3000): six CTAs of <= 560 samples hold 32-trait tiles (4 M tiles per warp) where four CTAs
+    // hold 16-trait ones, and 24 such clusters cover 144 SMs where 33 clusters of four cover 132.  Measured at n = 3000,
+    // p = 8000, q = 1500 (gpurun_out/r2d.log): 4 CTAs 11.24 ms, 5: 10.85, 6: 10.35, 7: 13.03, 8: 13.41.
+    if (!forced && n > 2688 && n <= 3360) ncta = 6;
     while (n > ncta * 112 * (ncta > 1 ? kMaxNTCl : kMaxNT)) {
+        if (forced) return false;
         ncta *= 2;
         if (ncta > kMaxCluster) return false;
     }

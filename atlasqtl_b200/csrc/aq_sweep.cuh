@@ -36,6 +36,16 @@
 #define AQ_T0() do { } while (0)
 #endif
 
+// Where the pending S phase is finished (accumulator chains added, partials stored, chain warp told) relative to the rank-8
+// update of the previous block: -1 = before the update starts (default); 0 / 2 / ... = after that many sample tiles of the
+// update, so that the S accumulators drain behind the first update DMMAs instead of idling the tensor pipe at the phase
+// boundary.  Measured on B200 (n = 1000, p = 50000, 2500 traits, gpurun_out/r2d.log): -1: 18.63 ms, 0: 19.01 ms, 2: 19.43 ms
+// -- the later the S partials reach the chain warp, the slower the sweep, although the chain warp idles 40 % of a block:
+// kept as a build-time knob for the record, off by default.
+#ifndef AQ_S_FINISH_AT
+#define AQ_S_FINISH_AT -1
+#endif
+
 namespace aq {
 
 struct SweepParams {
@@ -94,6 +104,9 @@ struct SweepCfg {
     static constexpr int kXS = kNPad + ((kNPad % 16 == 0) ? 8 : 0);  // tile row stride == 8 (mod 16) doubles
     static constexpr int kThreads = 16 * 32;  // warps 3 (chain) and 7 (helper) + 14 MMA warps (two of them on SMSP 3)
     static constexpr int kStages = 3;
+    // where the pending S phase is finished inside the rank-8 update (see AQ_S_FINISH_AT); with 3 or 4 M tiles per warp the
+    // S accumulators kept alive across the phase boundary would cost register spills in the MMA loops: never pipelined there
+    static constexpr int kSFin = (MT_ <= 2) ? AQ_S_FINISH_AT : -1;
     static constexpr size_t kTileDoubles = (size_t)kBlk * kXS + kTileTail;
     // S tiles in shared memory ([trait][8 SNP slots], partials and sums alike): row stride 8 doubles, the four 16-byte
     // pairs of a row XOR-swizzled by (trait >> 1) & 3 (sp_off), so that both the C-fragment stores of the MMA warps (lanes
@@ -301,7 +314,6 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
     __syncthreads();
     if (kCl) cluster_sync_all();  // every CTA's barriers are initialised before any remote arrive
 
-    const int nb = P.nb;
     const int nunits = P.ntiles * P.nseg;
     const int my_units = (nunits - group + ngroups - 1) / ngroups;
     const uint32_t tile_bytes = (uint32_t)(Cfg::kTileDoubles * sizeof(double));
@@ -368,15 +380,17 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     acc[mt][nt][0] = v.x;
                     acc[mt][nt][1] = v.y;
                 }
-            auto s_phase = [&](long gbi) {
+            // S phase of block gbi, in two halves.  s_issue: the split-K DMMAs of S'^T = R^T X_b into the accumulators sa.
+            // s_finish: add the accumulator chains, store the partials, tell the chain warp (directly after s_issue unless
+            // the AQ_S_FINISH_AT experiment moves it into the rank-8 update of the previous block).
+            constexpr int kSC = (MT >= 4) ? 1 : 2;   // accumulator chains per M tile
+            double sa[MT][2][2];
+            auto s_issue = [&](long gbi) {
                 const int stage = (int)(gbi % kStages);
                 AQ_T0();
                 mbar_wait(&full[stage], (uint32_t)((gbi / kStages) & 1));
                 AQ_T(10);
                 const double* xt = tiles + stage * Cfg::kTileDoubles;
-                // kSC accumulator chains per M tile: a dependent DMMA issues every ~26 cycles, the pipe takes one per 16
-                constexpr int kSC = (MT >= 4) ? 1 : 2;
-                double sa[MT][2][2];
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) sa[mt][0][0] = sa[mt][0][1] = sa[mt][1][0] = sa[mt][1][1] = 0.0;
 #pragma unroll
@@ -389,6 +403,9 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     for (int mt = 0; mt < MT; ++mt) dmma(sa[mt][kSC - 1][0], sa[mt][kSC - 1][1], acc[mt][nt][1], xb.y);
                 }
                 AQ_T(11);
+            };
+            auto s_finish = [&](long gbi) {
+                AQ_T0();
                 if (gbi > 0) mbar_wait(&sfree[0], (uint32_t)((gbi - 1) & 1));  // the previous block's partials have been read
                 AQ_T(12);
                 double* sp = spart + (size_t)ws * kT * Cfg::kSps + offP;
@@ -403,9 +420,14 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 if (lane == 0) mbar_arrive(&sdone[gbi & 1]);
                 AQ_T(13);
             };
-            if (P.mode == 0) s_phase(gb);
+            if (P.mode == 0) {
+                s_issue(gb);
+                s_finish(gb);
+            }
             for (int b = un.b0; b < un.b1; ++b, ++gb) {
-                if (P.mode == 0 && b + 1 < un.b1) s_phase(gb + 1);
+                const bool s_next = P.mode == 0 && b + 1 < un.b1;
+                if (s_next) s_issue(gb + 1);
+                if (Cfg::kSFin < 0 && s_next) s_finish(gb + 1);
                 // ---- rank-8 update with -Delta_b
                 const int stage = (int)(gb % kStages);
                 AQ_T0();
@@ -462,7 +484,9 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
 #pragma unroll
                         for (int mt = 0; mt < MT; ++mt) dmma(acc[mt][nt1][0], acc[mt][nt1][1], nd[mt][1], x1b);
                     }
+                    if (nt == Cfg::kSFin && s_next) s_finish(gb + 1);   // the S accumulators have drained meanwhile
                 }
+                if (Cfg::kSFin >= NT && s_next) s_finish(gb + 1);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[stage]);
                 AQ_T(15);
