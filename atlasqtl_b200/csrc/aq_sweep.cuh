@@ -127,8 +127,8 @@ struct SweepCfg {
     // cluster variant only: followers' reduced S tiles and squared-norm partials land in the leader's shared memory
     static constexpr size_t kRedDoubles = kCl ? (size_t)2 * (kMaxCluster - 1) * kT * kSps : 0;
     static constexpr size_t kRsqAllDoubles = kCl ? (size_t)(kMaxCluster - 1) * kT : 0;
-    // full, empty, sdone, dready, dcons, sred, rsqbar, inready, sfree
-    static constexpr int kNumBars = 2 * kStages + 2 + 2 + 2 + 2 + 1 + 2 + 1;
+    // full, empty, dready, dcons, sred, rsqbar, inready, sfree, sdone [2][4]
+    static constexpr int kNumBars = 2 * kStages + 2 + 2 + 2 + 1 + 2 + 1 + 8;
     static constexpr size_t kSmemBytes = (kStages * kTileDoubles + kSpartDoubles + kSsumDoubles + kDbufDoubles + kRsqDoubles +
                                           kIoDoubles + kStgDoubles + kRedDoubles + kRsqAllDoubles) *
                                              sizeof(double) +
@@ -174,25 +174,33 @@ __device__ __forceinline__ void group_sums(double (&v)[N], int lane, int top_bit
 // Lane layout: trait `tsum`, and with <= 16 traits per tile the two half-warps split the partials of a trait between them.
 // On return every lane holds the complete S row of its trait.  Called by the chain warp (single CTA) or the helper warp.
 template <class Cfg>
-__device__ __forceinline__ void sum_s_partials(double (&s)[kBlk], const double* spart, const double* red, uint64_t* sfree,
-                                               uint64_t* sred, long gb, int ncta, int lane, int tsum) {
+__device__ __forceinline__ void sum_s_partials(double (&s)[kBlk], const double* spart, const double* red, uint64_t* sdone,
+                                               uint64_t* sfree, uint64_t* sred, long gb, int ncta, int lane, int tsum) {
     constexpr int WS = Cfg::WS, kT = Cfg::kT;
+    static_assert(WS == 14, "MMA warp i sits on SMSP i % 3 for i < 12, warps 12 and 13 on SMSP 3");
     constexpr int kH = (kT <= 16) ? 2 : 1;
-    constexpr int kW0 = (WS + kH - 1) / kH;
     const int half = (kH == 2) ? (lane >> 4) : 0;
+    const uint32_t par = (uint32_t)((gb >> 1) & 1);
 #pragma unroll
     for (int t = 0; t < kBlk; ++t) s[t] = 0.0;
+    auto add = [&](int w) {
 #pragma unroll
-    for (int w2 = 0; w2 < kW0; ++w2) {
-        const int w = half * kW0 + w2;
-        if (kH == 1 || w < WS) {
-#pragma unroll
-            for (int t = 0; t < kBlk; t += 2) {
-                const double2 v = *reinterpret_cast<const double2*>(spart + w * kT * Cfg::kSps + sp_off(tsum, t));
-                s[t] += v.x;
-                s[t + 1] += v.y;
-            }
+        for (int t = 0; t < kBlk; t += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(spart + w * kT * Cfg::kSps + sp_off(tsum, t));
+            s[t] += v.x;
+            s[t + 1] += v.y;
         }
+    };
+    // group order: SMSP 3 first (its two MMA warps share the pipe with nobody and deliver early), then SMSP 0, 1, 2.  Fixed
+    // order whatever the arrival times: deterministic.
+    mbar_wait(&sdone[(gb & 1) * 4 + 3], par);
+    if (kH == 2) add(12 + half);
+    else { add(12); add(13); }
+#pragma unroll
+    for (int g4 = 0; g4 < 3; ++g4) {
+        mbar_wait(&sdone[(gb & 1) * 4 + g4], par);
+        if (kH == 2) { add(g4 + 6 * half); add(g4 + 6 * half + 3); }
+        else { add(g4); add(g4 + 3); add(g4 + 6); add(g4 + 9); }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&sfree[0]);  // the MMA warps may overwrite the partials
@@ -274,13 +282,15 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
     uint64_t* bars = reinterpret_cast<uint64_t*>(rsq_all + Cfg::kRsqAllDoubles);
     uint64_t* full = bars;                       // [kStages]  tile landed (tx bytes)
     uint64_t* empty = bars + kStages;            // [kStages]  MMA warps released the tile
-    uint64_t* sdone = bars + 2 * kStages;        // [2]  this CTA's MMA warps wrote their S partials
-    uint64_t* dready = bars + 2 * kStages + 2;   // [2]  chain warp published -Delta (in every CTA of the cluster)
-    uint64_t* dcons = bars + 2 * kStages + 4;    // [2]  mode 1 only, leader: all MMA warps consumed -Delta buffer
-    uint64_t* sred = bars + 2 * kStages + 6;     // [2]  leader: followers delivered their reduced S tiles
-    uint64_t* rsqbar = bars + 2 * kStages + 8;   // [1]  leader: followers delivered their squared-norm partials
-    uint64_t* inready = bars + 2 * kStages + 9;  // [2]  helper warp staged S and the block's inputs for the chain
-    uint64_t* sfree = bars + 2 * kStages + 11;   // [1]  helper / reducer warp has read the S partials of a block
+    uint64_t* dready = bars + 2 * kStages;       // [2]  chain warp published -Delta (in every CTA of the cluster)
+    uint64_t* dcons = bars + 2 * kStages + 2;    // [2]  mode 1 only, leader: all MMA warps consumed -Delta buffer
+    uint64_t* sred = bars + 2 * kStages + 4;     // [2]  leader: followers delivered their reduced S tiles
+    uint64_t* rsqbar = bars + 2 * kStages + 6;   // [1]  leader: followers delivered their squared-norm partials
+    uint64_t* inready = bars + 2 * kStages + 7;  // [2]  helper warp staged S and the block's inputs for the chain
+    uint64_t* sfree = bars + 2 * kStages + 9;    // [1]  helper / reducer warp has read the S partials of a block
+    // [2][4]  this CTA's MMA warps wrote their S partials, one barrier per SM sub-partition (the four warps of SMSP 0, 1, 2,
+    // the two of SMSP 3): whoever sums the partials takes them group by group as they complete instead of after the last
+    uint64_t* sdone = bars + 2 * kStages + 10;
 
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef AQ_TIMING
@@ -301,7 +311,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], Cfg::kMmaWarps); }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&sdone[s], Cfg::kMmaWarps);
+            for (int g4 = 0; g4 < 4; ++g4) mbar_init(&sdone[s * 4 + g4], g4 < 3 ? 4 : Cfg::kMmaWarps - 12);
             mbar_init(&dready[s], 1);
             mbar_init(&dcons[s], Cfg::kMmaWarps * ncta);
             mbar_init(&sred[s], 1);
@@ -417,7 +427,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     *reinterpret_cast<double2*>(sp + mt * 8 * Cfg::kSps) = v;
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sdone[gbi & 1]);
+                if (lane == 0) mbar_arrive(&sdone[(gbi & 1) * 4 + smsp]);
                 AQ_T(13);
             };
             if (P.mode == 0) {
@@ -563,7 +573,8 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 if (gb >= 2) mbar_wait(&dready[gb & 1], (uint32_t)(((gb >> 1) - 1) & 1));  // the phase of block gb - 2 is over
                 if (lane == 0) mbar_arrive_expect_tx(&dready[gb & 1], Cfg::kDeltaBytes);
                 if (P.mode != 0) continue;
-                mbar_wait(&sdone[gb & 1], (uint32_t)((gb >> 1) & 1));
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) mbar_wait(&sdone[(gb & 1) * 4 + g4], (uint32_t)((gb >> 1) & 1));
                 double s[kBlk];
 #pragma unroll
                 for (int t = 0; t < kBlk; ++t) s[t] = 0.0;
@@ -671,10 +682,9 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     }
                     if (blk + 1 < un.b1) stage_rows(blk + 1);
                     if (!Cfg::kChainSums) {
-                        mbar_wait(&sdone[g & 1], (uint32_t)((g >> 1) & 1));
                         AQ_T(4);
                         double s[kBlk];
-                        sum_s_partials<Cfg>(s, spart, red, sfree, sred, g, ncta, lane, tls);
+                        sum_s_partials<Cfg>(s, spart, red, sdone, sfree, sred, g, ncta, lane, tls);
                         if (half == 0 && active) {
 #pragma unroll
                             for (int t = 0; t < kBlk; t += 2) {
@@ -824,9 +834,8 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     if (Cfg::kChainSums) {
                         // S = X_b' R: this warp sums the split-K partials itself the moment the MMA warps have delivered
                         // them; no other warp sits between the tensor work and the recurrence
-                        mbar_wait(&sdone[gb & 1], (uint32_t)((gb >> 1) & 1));
                         AQ_T(0);
-                        sum_s_partials<Cfg>(s, spart, red, sfree, sred, gb, ncta, lane, tsum);
+                        sum_s_partials<Cfg>(s, spart, red, sdone, sfree, sred, gb, ncta, lane, tsum);
                     } else {
                         AQ_T(0);
                         const double* sp0 = ssum + (size_t)(gb & 1) * kT * Cfg::kSps;
