@@ -128,14 +128,22 @@ def _lentz_vecwide(xu, eps1, eps2):
     return f_p
 
 
-def Q_approx_vec(x, eps1=1e-30, eps2=1e-7):
+def Q_approx_vec(x, eps1=1e-30, eps2=1e-7, only=None):
     """E1(x) exp(x): gsl::expint_E1 branch for x <= 1, modified Lentz for x > 1 with the reference's
-    vector-wide stopping rule (R/utils.R:380-423)."""
+    vector-wide stopping rule (R/utils.R:380-423).  only = (j0, j1): the element-wise E1 branch is evaluated for the
+    entries [j0, j1) alone (the others are left at 0); the Lentz branch always sees the whole vector, as its stopping
+    rule demands."""
     x = np.asarray(x, dtype=np.float64)
-    out = np.empty_like(x)
+    out = np.zeros_like(x)
     lo = x <= 1
-    if lo.any():
-        out[lo] = _pmap(lambda v: sp.exp1(v) * np.exp(v), x[lo])
+    if only is not None:
+        inside = np.zeros(x.shape, dtype=bool)
+        inside[only[0]:only[1]] = True
+        lo_eval = lo & inside
+    else:
+        lo_eval = lo
+    if lo_eval.any():
+        out[lo_eval] = _pmap(lambda v: sp.exp1(v) * np.exp(v), x[lo_eval])
     if (~lo).any():
         xu = np.ascontiguousarray(x[~lo])
         out[~lo] = 1 / (xu + 1 + _lentz_vecwide(xu, eps1, eps2))
@@ -403,14 +411,22 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
 
             # The horseshoe scale update (:241-254) reads only the PREVIOUS theta_vb / sig2_theta_vb / sig02_inv_vb, so its
             # p-vector special functions (incomplete gammas, E1 / Lentz) run on a host thread while the GPU sweeps; the
-            # statements and their operands are unchanged, only the wall-clock position moves.
+            # statements and their operands are unchanged, only the wall-clock position moves.  With several ranks every
+            # rank evaluates the element-wise special functions on ITS slice of the p SNPs only and the slices are
+            # exchanged in the sweep's all-reduce (a sum with zeros elsewhere: exact, identical on all ranks) -- 8 ranks
+            # each computing all p values on a shared host made every rank wait for this update once the sweep took 18 ms.
+            # The Lentz branch is evaluated on the whole vector by everybody: its stopping rule is vector-wide (R/utils.R:402).
+            j0, j1 = (comm.rank * p) // comm.world_size, ((comm.rank + 1) * p) // comm.world_size
+
             def _hs_scale(c_s=c_s, theta=theta_vb, s2t=sig2_theta_vb, s02=sig02_inv_vb, ann=annealing and anneal_scale):
                 th2_ = theta ** 2 + s2t - 2 * theta * m0 + m0 ** 2
                 L_ = c_s * s02 * shr_fac_inv * th2_ / 2 / df  # :241
+                part = np.zeros(p)
                 if ann:
-                    return L_, None, update_annealed_lam2_inv_vb_(L_, c_s, df)  # :246
-                Q_ = Q_approx_vec(L_)  # :250
-                return L_, Q_, 1 / (Q_ * L_) - 1  # :254
+                    part[j0:j1] = update_annealed_lam2_inv_vb_(L_[j0:j1], c_s, df)  # :246
+                else:
+                    part[j0:j1] = Q_approx_vec(L_, only=(j0, j1))[j0:j1]  # :250
+                return L_, ann, part
             hs_future = _background().submit(_hs_scale)
 
             _lap("pre")
@@ -425,6 +441,9 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
             _lap("sweep")
             colsum_m2 = m2_of(sums)  # :235
             local = [sums["colsum_gam"].sum(), np.dot(tau_vb, colsum_m2)]
+            if comm.world_size > 1:  # this rank's slice of the horseshoe p-vector rides in the same message
+                L_vb, hs_ann, hs_part = hs_future.result()
+                local = np.concatenate([local, hs_part])
             if (comm.world_size > 1 and callable(getattr(comm, "allreduce_sum_device", None))
                     and hasattr(ctx, "rowsums_zpart_dev")):
                 # the row sums never visit the host before the all-reduce: NCCL reduces the library's device buffer in
@@ -432,13 +451,13 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
                 ptr = ctx.rowsums_zpart_dev()
                 _lap("rowsums")
                 rowsum_zpart = comm.allreduce_sum_device(ptr, p)
-                glob = comm.allreduce_sum(np.array(local))
-                sum_gam, tau_dot_m2 = float(glob[0]), float(glob[1])
+                glob = comm.allreduce_sum(np.asarray(local))
+                sum_gam, tau_dot_m2, hs_vec = float(glob[0]), float(glob[1]), glob[2:]
             else:
                 rows = ctx.rowsums_zpart()
                 _lap("rowsums")
                 glob = comm.allreduce_sum(np.concatenate([rows, local]))
-                rowsum_zpart, sum_gam, tau_dot_m2 = glob[:p], float(glob[p]), float(glob[p + 1])
+                rowsum_zpart, sum_gam, tau_dot_m2, hs_vec = glob[:p], float(glob[p]), float(glob[p + 1]), glob[p + 2:]
             _lap("allreduce")
 
             sqrt_c = 1.0 if abs(c - 1) < ALL_EQUAL_TOL else math.sqrt(c)  # R/update_vb.R:219-229
@@ -446,10 +465,14 @@ def atlasqtl_global_local_core_(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbo
             colsums_Z = sums["colsum_zpart"] / sqrt_c + theta_vb.sum() + p * zeta_vb
 
             rho_xi_inv_vb = c_s * (A2_inv + sig02_inv_vb)  # :242
-            L_vb, Q_new, lam2_inv_vb = hs_future.result()
+            if comm.world_size == 1:
+                L_vb, hs_ann, hs_vec = hs_future.result()
             _lap("hs_wait")
-            if Q_new is not None:
-                Q_app = Q_new
+            if hs_ann:
+                lam2_inv_vb = hs_vec  # :246
+            else:
+                Q_app = hs_vec  # :250
+                lam2_inv_vb = 1 / (Q_app * L_vb) - 1  # :254
             xi_inv_vb = nu_xi_inv_vb / rho_xi_inv_vb  # :276
             prior_prec = sig02_inv_vb * lam2_inv_vb * shr_fac_inv
             sig2_theta_vb = 1 / (c * (q_total + prior_prec))  # :278

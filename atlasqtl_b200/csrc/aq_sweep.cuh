@@ -170,12 +170,12 @@ __device__ __forceinline__ void group_sums(double (&v)[N], int lane, int top_bit
     }
 }
 
-// S = X_b' R of one block: sums this CTA's WS split-K partials and, on a cluster leader, the tiles the other CTAs shipped.
-// Lane layout: trait `tsum`, and with <= 16 traits per tile the two half-warps split the partials of a trait between them.
-// On return every lane holds the complete S row of its trait.  Called by the chain warp (single CTA) or the helper warp.
+// This CTA's part of S = X_b' R of one block: sums the WS split-K partials of its MMA warps, SM sub-partition by
+// sub-partition as their barriers complete.  Lane layout: trait `tsum`, and with <= 16 traits per tile the two half-warps
+// split the partials of a trait between them (the caller adds the halves).  Frees the partial buffer when done.
 template <class Cfg>
-__device__ __forceinline__ void sum_s_partials(double (&s)[kBlk], const double* spart, const double* red, uint64_t* sdone,
-                                               uint64_t* sfree, uint64_t* sred, long gb, int ncta, int lane, int tsum) {
+__device__ __forceinline__ void sum_own_partials(double (&s)[kBlk], const double* spart, uint64_t* sdone, uint64_t* sfree,
+                                                 long gb, int lane, int tsum) {
     constexpr int WS = Cfg::WS, kT = Cfg::kT;
     static_assert(WS == 14, "MMA warp i sits on SMSP i % 3 for i < 12, warps 12 and 13 on SMSP 3");
     constexpr int kH = (kT <= 16) ? 2 : 1;
@@ -204,6 +204,17 @@ __device__ __forceinline__ void sum_s_partials(double (&s)[kBlk], const double* 
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&sfree[0]);  // the MMA warps may overwrite the partials
+}
+
+// S = X_b' R of one block: this CTA's partials and, on a cluster leader, the tiles the other CTAs shipped.
+// On return every lane holds the complete S row of its trait.  Called by the chain warp (single CTA) or the helper warp.
+template <class Cfg>
+__device__ __forceinline__ void sum_s_partials(double (&s)[kBlk], const double* spart, const double* red, uint64_t* sdone,
+                                               uint64_t* sfree, uint64_t* sred, long gb, int ncta, int lane, int tsum) {
+    constexpr int kT = Cfg::kT;
+    constexpr int kH = (kT <= 16) ? 2 : 1;
+    const int half = (kH == 2) ? (lane >> 4) : 0;
+    sum_own_partials<Cfg>(s, spart, sdone, sfree, gb, lane, tsum);
     if (Cfg::kCl && ncta > 1) {  // + the other sample slices, already reduced (and stored here) by their CTAs
         if (lane == 0) mbar_arrive_expect_tx(&sred[gb & 1], (uint32_t)(ncta - 1) * Cfg::kDeltaBytes);
         mbar_wait(&sred[gb & 1], (uint32_t)((gb >> 1) & 1));
@@ -559,7 +570,6 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
         // no fence).  With <= 16 traits per tile the two half-warps split the work.
         constexpr int kH = (kT <= 16) ? 2 : 1;
         constexpr int kTP = kBlk / kH;
-        constexpr int kW0 = (WS + kH - 1) / kH;
         const int half = (kH == 2) ? (lane >> 4) : 0;
         const int tl = (kH == 2) ? (lane & 15) : lane;
         const bool active = tl < kT;
@@ -573,25 +583,8 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 if (gb >= 2) mbar_wait(&dready[gb & 1], (uint32_t)(((gb >> 1) - 1) & 1));  // the phase of block gb - 2 is over
                 if (lane == 0) mbar_arrive_expect_tx(&dready[gb & 1], Cfg::kDeltaBytes);
                 if (P.mode != 0) continue;
-#pragma unroll
-                for (int g4 = 0; g4 < 4; ++g4) mbar_wait(&sdone[(gb & 1) * 4 + g4], (uint32_t)((gb >> 1) & 1));
                 double s[kBlk];
-#pragma unroll
-                for (int t = 0; t < kBlk; ++t) s[t] = 0.0;
-#pragma unroll
-                for (int w2 = 0; w2 < kW0; ++w2) {
-                    const int w = half * kW0 + w2;
-                    if (kH == 1 || w < WS) {
-#pragma unroll
-                        for (int t = 0; t < kBlk; t += 2) {
-                            const double2 v = *reinterpret_cast<const double2*>(spart + w * kT * Cfg::kSps + sp_off(tls, t));
-                            s[t] += v.x;
-                            s[t + 1] += v.y;
-                        }
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sfree[0]);  // the MMA warps may overwrite the partials
+                sum_own_partials<Cfg>(s, spart, sdone, sfree, gb, lane, tls);
                 if (kH == 2) {
 #pragma unroll
                     for (int t = 0; t < kBlk; ++t) s[t] += __shfl_xor_sync(0xffffffffu, s[t], 16);

@@ -119,31 +119,42 @@ def make_workload(name, k_first, k_last, seed=123, threads=None, force_dense=Fal
     with ThreadPoolExecutor(threads) as ex:
         list(ex.map(gen, starts))
     ql = k_last - k_first
-    Y = X_act @ beta[:, k_first:k_last] + np.random.default_rng(seed + 1 + k_first).normal(size=(n, ql))
-    if not packed:
-        Y = Y - Y.mean(axis=0)   # (packed path: centred on the device, like scale(Y, scale = FALSE) R/prepare_atlasqtl.R:83)
-    Y = np.asfortranarray(Y)
+    # Everything per-trait is drawn on a FIXED global grid of trait chunks (each with its own generator stream), so that the
+    # data do not depend on how the traits are sharded: the `check` values of runs at different GPU counts are comparable.
+    tchunk = 64
+
+    def trait_chunks():
+        for c0 in range((k_first // tchunk) * tchunk, k_last, tchunk):
+            lo, hi = max(c0, k_first), min(c0 + tchunk, k_last, q)
+            yield c0, lo - c0, hi - c0, lo - k_first, hi - k_first   # chunk start, columns inside it, columns of the slab
+
+    Y = np.empty((n, ql), order="F")
+    gam = np.empty((p, ql), order="F")
+    mu = np.empty((p, ql), order="F")
     e_p = max(1.0, float(pat.sum(axis=0).mean()))
     p0 = (e_p, max(10.0, 2.0 * e_p))  # (mean, variance) of the prior number of active SNPs per trait
     t02 = hyper_init._solve_t02(p, p0)
     n0 = float(hyper_init.get_mu(p0[0], t02, p))
-    tau0 = 1.0  # ~ 1 / median var(Y_k) of the recipe (unit noise); fixed so that every rank uses the same value
-    hyper = hyper_init.set_hyper(q, p, tau0, 1.0, n0, 1e-2, 1.0, t02)
-    # auto_set_init_ distributions (R/set_hyper_init.R:388-405), drawn slab-wise in parallel
-    gam = np.empty((p, ql), order="F")
-    mu = np.empty((p, ql), order="F")
     sd0 = 1e-4 + t02
-    chunk = max(1, min(256, (64 << 20) // (4 * p)))
 
-    def fill(k0):
-        r = np.random.default_rng([seed, 7, k_first + k0])
-        k1 = min(ql, k0 + chunk)
-        z = r.standard_normal((k1 - k0, p), dtype=np.float32)
-        gam[:, k0:k1] = sp.ndtr(n0 + sd0 * z).T
-        mu[:, k0:k1] = r.standard_normal((k1 - k0, p), dtype=np.float32).T
+    def fill(ch):
+        c0, a, b, lo, hi = ch
+        r = np.random.default_rng([seed, 7, c0])
+        noise = r.standard_normal((tchunk, n))   # auto_set_init_ distributions (R/set_hyper_init.R:388-405) below
+        Y[:, lo:hi] = X_act @ beta[:, k_first + lo:k_first + hi] + noise[a:b].T
+        for k in range(tchunk):   # one trait at a time: bounded scratch whatever p is
+            z = r.standard_normal(p, dtype=np.float32)
+            m = r.standard_normal(p, dtype=np.float32)
+            if a <= k < b:
+                gam[:, lo + k - a] = sp.ndtr(n0 + sd0 * z)
+                mu[:, lo + k - a] = m
 
     with ThreadPoolExecutor(threads) as ex:
-        list(ex.map(fill, range(0, ql, chunk)))
+        list(ex.map(fill, list(trait_chunks())))
+    if not packed:
+        Y -= Y.mean(axis=0)   # (packed path: centred on the device, like scale(Y, scale = FALSE) R/prepare_atlasqtl.R:83)
+    tau0 = 1.0  # ~ 1 / median var(Y_k) of the recipe (unit noise); fixed so that every rank uses the same value
+    hyper = hyper_init.set_hyper(q, p, tau0, 1.0, n0, 1e-2, 1.0, t02)
     r = np.random.default_rng(seed + 3)
     sig02_inv = float(r.gamma(shape=max(p, q), scale=1.0))
     init = dict(q_init=q, p_init=p, gam_vb=gam, mu_beta_vb=mu, sig02_inv_vb=sig02_inv,
