@@ -73,6 +73,36 @@ bool pick_nt(int nt, bool cl, int ncta, CfgInfo* out) {
     return false;
 }
 
+// ---- missing-response variants (SweepCfg<2, NT, clustered, true>, ids 1000 + ...): 16-trait tiles, and fewer sample
+// tiles per warp than the dense kernel so that the per-trait Gram band buffers (32 KB) fit beside the X tile ring:
+// NT <= 7 in one CTA (n <= 784), NT <= 6 in clusters of 2 / 4 / 6 / 8 CTAs (n <= 5376).
+constexpr int kMaxNTMis = 7, kMaxNTMisCl = 6;
+template <int NT, bool CL>
+using CfgMis = SweepCfg<2, NT, CL, true>;
+template <int NT>
+bool pick_nt_mis(int nt, bool cl, int ncta, CfgInfo* out) {
+    if (nt == NT) {
+        if (!cl) *out = info<CfgMis<NT, false>>(1000 + NT, 1);
+        else if constexpr (NT <= kMaxNTMisCl) *out = info<CfgMis<NT, true>>(1100 + NT, ncta);
+        else return false;
+        return true;
+    }
+    if constexpr (NT < kMaxNTMis) return pick_nt_mis<NT + 1>(nt, cl, ncta, out);
+    return false;
+}
+bool pick_cfg_mis(int n, CfgInfo* out) {
+    const char* fc = std::getenv("AQ_FORCE_CLUSTER");
+    int ncta = fc ? std::atoi(fc) : 0;
+    if (!(ncta >= 2 && ncta <= kMaxCluster)) {
+        ncta = 0;
+        for (int cand : {1, 2, 4, 6, 8})
+            if (n <= cand * 112 * (cand > 1 ? kMaxNTMisCl : kMaxNTMis)) { ncta = cand; break; }
+        if (!ncta) return false;
+    } else if (n > ncta * 112 * kMaxNTMisCl) return false;
+    const int nt = (n + 112 * ncta - 1) / (112 * ncta);
+    return pick_nt_mis<1>(nt, ncta > 1, ncta, out);
+}
+
 bool pick_cfg(int n, CfgInfo* out) {
     // development knob: AQ_FORCE_CLUSTER=2..8 selects the sample-split cluster kernel with that many CTAs per cluster
     // (even where one CTA suffices); by default the smallest power of two that holds the samples
@@ -116,6 +146,13 @@ struct aq_ctx {
     unsigned long long* mask = nullptr;
     double *xnsq = nullptr, *n_obs = nullptr, *mis_out = nullptr;
     double* sig2tab = nullptr;  // explicit p x q sig2_beta_vb (stateless coreDualMisLoop entry only)
+    // tile-structured missing-response path (aq_sweep.cuh, MIS variant): observed-sample bit matrix, CSR lists of the
+    // missing samples per trait, per-trait Gram band table, the two per-sweep p x q tables
+    bool mis_tile = false;
+    unsigned long long* mbits = nullptr;
+    int mwords = 0;
+    int *mis_off_dev = nullptr, *mis_idx_dev = nullptr;
+    double *gk = nullptr, *atab = nullptr, *ltab = nullptr;
     bool has_mis = false;
     double* rowpart = nullptr;      // [rowpart_cap][p_pad] per-tile row sums of gam W + I0 left by the last aq_sweep
     int rowpart_cap = 0, rowpart_rows = 0;   // rows allocated / rows the last sweep wrote (0: not valid)
@@ -158,6 +195,8 @@ struct aq_prep {
 };
 
 namespace {
+
+int build_gk(aq_ctx* c);   // (missing-response tile path, defined with aq_set_missing)
 
 // Launch attributes of one kernel configuration on this context's device: set once per context (not in function statics:
 // the cluster size is a run-time value of the same template instance, and contexts live on several devices / threads).
@@ -335,6 +374,30 @@ int launch_sweep_cfg(aq_ctx* c, const SweepParams& P) {
     return AQ_OK;
 }
 
+// Missing-response variant: one launch, one unit per 16-trait tile (no segments, no 8-trait tail variant).
+template <int NT, bool CL>
+int launch_sweep_mis_cfg(aq_ctx* c, const SweepParams& P) {
+    using Main = CfgMis<NT, CL>;
+    int rc = prepare_sweep_t<Main>(c, 0);
+    if (rc != AQ_OK) return rc;
+    c->last_nseg = 1;
+    c->rowpart_rows = 0;
+    AQ_CUDA(cudaEventRecord(c->ev0, c->stream));
+    rc = launch_sweep_t<Main>(c, 0, P, c->ntiles, 0);
+    if (rc != AQ_OK) return rc;
+    AQ_CUDA(cudaEventRecord(c->ev1, c->stream));
+    return AQ_OK;
+}
+
+template <int NT>
+int launch_sweep_mis_id(aq_ctx* c, const SweepParams& P) {
+    if (c->cfg.id == 1000 + NT) return launch_sweep_mis_cfg<NT, false>(c, P);
+    if constexpr (NT <= kMaxNTMisCl)
+        if (c->cfg.id == 1100 + NT) return launch_sweep_mis_cfg<NT, true>(c, P);
+    if constexpr (NT < kMaxNTMis) return launch_sweep_mis_id<NT + 1>(c, P);
+    return fail(AQ_EUNSUPPORTED, "no kernel configuration (missing responses)");
+}
+
 template <int NT>
 int launch_sweep_id(aq_ctx* c, const SweepParams& P) {
     if (c->cfg.id == NT) return launch_sweep_cfg<NT, false>(c, P);
@@ -375,6 +438,14 @@ int launch_sweep(aq_ctx* c, int mode, double cc, double log_sig2_inv) {
     P.rowpart = nullptr;
     P.rowpart_base = 0;
     P.p_pad = c->p_pad;
+    P.mbits = c->mbits;
+    P.mwords = c->mwords;
+    P.xnsq = c->xnsq;
+    P.atab = c->atab;
+    P.ltab = c->ltab;
+    P.gk = c->gk;
+    P.mis_out = c->mis_out;
+    if (c->mis_tile) P.rsq = c->mis_out + (size_t)kMisRsq * c->q_pad;
     P.mode = mode;
     P.nseg = 1;
     P.seg_len = c->nb;
@@ -391,8 +462,8 @@ int launch_sweep(aq_ctx* c, int mode, double cc, double log_sig2_inv) {
         P.timing = tbuf;
     }
 #endif
+    if (c->cfg.id >= 1000) return launch_sweep_mis_id<1>(c, P);
     return launch_sweep_id<1>(c, P);
-
 }
 
 int upload_pxq(aq_ctx* c, const double* host, double* dev) {
@@ -528,6 +599,11 @@ int aq_destroy(aq_ctx* c) {
     if (c->order_dev) cudaFree(c->order_dev);
     if (c->seg_done) cudaFree(c->seg_done);
     if (c->mask) cudaFree(c->mask);
+    if (c->mbits) cudaFree(c->mbits);
+    if (c->mis_off_dev) cudaFree(c->mis_off_dev);
+    if (c->mis_idx_dev) cudaFree(c->mis_idx_dev);
+    for (double* b : {c->gk, c->atab, c->ltab})
+        if (b) cudaFree(b);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     for (double* b : {c->sig2tab, c->xnsq, c->n_obs, c->mis_out, c->sel_partial, c->rowpart, c->snap_gam, c->snap_mu, c->stage2})
         if (b) cudaFree(b);
@@ -564,10 +640,12 @@ int create_impl(aq_ctx** out, int device, int n, int p, int q_local, const doubl
     c->cfg = cfg;
     c->sm_count = sm;
     c->p_pad = (p + kBlk - 1) / kBlk * kBlk;
-    c->q_pad = (q_local + cfg.kT - 1) / cfg.kT * cfg.kT;
+    // leading dimension of the p x q arrays: a multiple of every tile width (16 / 24 / 32 traits, 96 = their lcm), so that a
+    // context can change its kernel configuration (missing responses use 16-trait tiles) without re-laying them out
+    c->q_pad = (q_local + 95) / 96 * 96;
     c->nb = c->p_pad / kBlk;
     c->ld_resid = cfg.n_pad * cfg.ncta;
-    c->ntiles = c->q_pad / cfg.kT;
+    c->ntiles = (q_local + cfg.kT - 1) / cfg.kT;
     const size_t pq = (size_t)c->p_pad * c->q_pad;
     c->stage_cols = (int)std::max<size_t>(1, std::min<size_t>((size_t)q_local, ((size_t)256 << 20) / (sizeof(double) * (size_t)p)));
     c->n_partials = (size_t)((c->q + 255) / 256) * ((c->p + kTabRowsPerBlock - 1) / kTabRowsPerBlock);
@@ -932,6 +1010,7 @@ int aq_set_order(aq_ctx* c, const int32_t* shuffled_ind) {
     if (!c->xraw) return fail(AQ_ESTATE, "aq_set_order: a new order needs the untiled X, which aq_release_x freed");
     c->order.swap(ord);
     int rc = retile(c);
+    if (rc == AQ_OK && c->mis_tile) rc = build_gk(c);   // the per-trait Gram band follows the blocks of the order
     if (rc != AQ_OK) return rc;
     AQ_CUDA(cudaStreamSynchronize(c->stream));
     return AQ_OK;
@@ -1162,12 +1241,133 @@ int fetch_mis(aq_ctx* c, const int* rows, double* const* outs, int nout) {
 }
 }  // namespace
 
+}  // extern "C"
+
+namespace {
+// (Re)build the per-trait Gram band table and X_norm_sq of the tile path: depends on the masks and on the sweep order.
+int build_gk(aq_ctx* c) {
+    const int ntiles = c->ntiles;
+    AQ_CUDA(cudaMemsetAsync(c->xnsq, 0, sizeof(double) * (size_t)c->p_pad * c->q_pad, c->stream));
+    gk_build_kernel<<<dim3(c->nb, ntiles), 128, 0, c->stream>>>(c->xtiles, c->nb, c->cfg.ncta, c->cfg.n_pad, c->cfg.xs,
+                                                                c->cfg.tile_doubles, c->mis_off_dev, c->mis_idx_dev, c->q,
+                                                                c->q_pad, c->gk, c->xnsq);
+    AQ_CUDA(cudaGetLastError());
+    c->launches++;
+    return AQ_OK;
+}
+
+// Tile-structured missing-response path: switch the context to the MIS kernel configuration for its n (16-trait tiles,
+// smaller sample tiles: the X tile images, Y and the residual are laid out again), build the observed-sample bit matrix,
+// the CSR lists of missing samples and the per-trait Gram band table.
+int set_missing_tile(aq_ctx* c, const CfgInfo& cfgm, const double* mis_pat, double* n_obs) {
+    const size_t pq = (size_t)c->p_pad * c->q_pad;
+    const int n = c->n, q = c->q;
+    if (cfgm.id != c->cfg.id || cfgm.ncta != c->cfg.ncta) {
+        const int ld_new = cfgm.n_pad * cfgm.ncta;
+        double *y_new = nullptr, *r_new = nullptr, *t_new = nullptr;
+        AQ_CUDA(cudaStreamSynchronize(c->stream));
+        AQ_CUDA(cudaFree(c->xtiles));
+        c->xtiles = nullptr;
+        AQ_CUDA(cudaFree(c->resid));
+        c->resid = nullptr;
+        AQ_CUDA(cudaMalloc((void**)&y_new, sizeof(double) * (size_t)c->q_pad * ld_new));
+        AQ_CUDA(cudaMemsetAsync(y_new, 0, sizeof(double) * (size_t)c->q_pad * ld_new, c->stream));
+        AQ_CUDA(cudaMemcpy2DAsync(y_new, sizeof(double) * ld_new, c->ymat, sizeof(double) * c->ld_resid, sizeof(double) * n, q,
+                                  cudaMemcpyDeviceToDevice, c->stream));
+        AQ_CUDA(cudaStreamSynchronize(c->stream));
+        AQ_CUDA(cudaFree(c->ymat));
+        c->ymat = y_new;
+        AQ_CUDA(cudaMalloc((void**)&r_new, sizeof(double) * (size_t)c->q_pad * ld_new));
+        c->resid = r_new;
+        AQ_CUDA(cudaMalloc((void**)&t_new, sizeof(double) * (size_t)c->nb * cfgm.ncta * cfgm.tile_doubles));
+        c->xtiles = t_new;
+        c->cfg = cfgm;
+        c->ld_resid = ld_new;
+        c->ntiles = (q + cfgm.kT - 1) / cfgm.kT;
+        c->attr_done[0] = c->attr_done[1] = false;
+        if (c->seg_done) { cudaFree(c->seg_done); c->seg_done = nullptr; }
+        if (c->rowpart) { cudaFree(c->rowpart); c->rowpart = nullptr; }
+        c->rowpart_tried = true;   // (the tile path of the missing-response sweep streams the row sums)
+        int rc = retile(c);
+        if (rc != AQ_OK) return rc;
+    }
+    c->mwords = (c->ld_resid + 63) / 64;
+    if (c->mbits) { cudaFree(c->mbits); c->mbits = nullptr; }
+    AQ_CUDA(cudaMalloc((void**)&c->mbits, sizeof(unsigned long long) * (size_t)c->q_pad * c->mwords));
+    AQ_CUDA(cudaMemsetAsync(c->mbits, 0, sizeof(unsigned long long) * (size_t)c->q_pad * c->mwords, c->stream));
+    if (!c->xnsq) AQ_CUDA(cudaMalloc((void**)&c->xnsq, sizeof(double) * pq));
+    if (!c->atab) AQ_CUDA(cudaMalloc((void**)&c->atab, sizeof(double) * pq));
+    if (!c->ltab) AQ_CUDA(cudaMalloc((void**)&c->ltab, sizeof(double) * pq));
+    if (!c->n_obs) AQ_CUDA(cudaMalloc((void**)&c->n_obs, sizeof(double) * c->q_pad));
+    if (!c->mis_out) AQ_CUDA(cudaMalloc((void**)&c->mis_out, sizeof(double) * kMisOutputs * (size_t)c->q_pad));
+    AQ_CUDA(cudaMemsetAsync(c->atab, 0, sizeof(double) * pq, c->stream));
+    AQ_CUDA(cudaMemsetAsync(c->ltab, 0, sizeof(double) * pq, c->stream));
+    AQ_CUDA(cudaMemsetAsync(c->mis_out, 0, sizeof(double) * kMisOutputs * (size_t)c->q_pad, c->stream));
+    // the n x q pattern goes through the residual buffer (same [q][ld] orientation, ld >= n), which is rebuilt by set_state
+    double* tmp = c->resid;
+    AQ_CUDA(cudaMemcpyAsync(tmp, mis_pat, sizeof(double) * (size_t)n * q, cudaMemcpyHostToDevice, c->stream));
+    pack_bits_kernel<<<(q + 7) / 8, 256, 0, c->stream>>>(tmp, n, q, c->mwords, c->ld_resid, c->mbits, c->ymat, c->n_obs);
+    AQ_CUDA(cudaGetLastError());
+    c->launches++;
+    // CSR lists of the missing samples of every trait (rows of padding traits are empty)
+    std::vector<int32_t> off((size_t)c->q_pad + 1, 0), idx;
+    for (int k = 0; k < q; ++k) {
+        const double* col = mis_pat + (size_t)k * n;
+        for (int i = 0; i < n; ++i)
+            if (col[i] == 0.0) idx.push_back(i);
+        off[k + 1] = (int32_t)idx.size();
+    }
+    for (int k = q; k < c->q_pad; ++k) off[k + 1] = off[q];
+    if (c->mis_off_dev) { cudaFree(c->mis_off_dev); c->mis_off_dev = nullptr; }
+    if (c->mis_idx_dev) { cudaFree(c->mis_idx_dev); c->mis_idx_dev = nullptr; }
+    AQ_CUDA(cudaMalloc((void**)&c->mis_off_dev, sizeof(int32_t) * off.size()));
+    AQ_CUDA(cudaMalloc((void**)&c->mis_idx_dev, sizeof(int32_t) * std::max<size_t>(idx.size(), 1)));
+    AQ_CUDA(cudaMemcpyAsync(c->mis_off_dev, off.data(), sizeof(int32_t) * off.size(), cudaMemcpyHostToDevice, c->stream));
+    if (!idx.empty())
+        AQ_CUDA(cudaMemcpyAsync(c->mis_idx_dev, idx.data(), sizeof(int32_t) * idx.size(), cudaMemcpyHostToDevice, c->stream));
+    if (c->gk) { cudaFree(c->gk); c->gk = nullptr; }
+    AQ_CUDA(cudaMalloc((void**)&c->gk, sizeof(double) * (size_t)c->ntiles * c->nb * 128 * 16));
+    c->has_mis = true;
+    c->mis_tile = true;
+    c->have_state = false;
+    int rc = build_gk(c);
+    if (rc != AQ_OK) return rc;
+    if (n_obs) AQ_CUDA(cudaMemcpyAsync(n_obs, c->n_obs, sizeof(double) * q, cudaMemcpyDeviceToHost, c->stream));
+    AQ_CUDA(cudaStreamSynchronize(c->stream));   // (off / idx are host vectors: the copies must be through before they go)
+    return AQ_OK;
+}
+}  // namespace
+
+extern "C" {
+
 int aq_set_missing(aq_ctx* c, const double* mis_pat, double* n_obs) {
     if (!c || !mis_pat) return fail(AQ_EINVAL, "aq_set_missing: NULL argument");
-    if (c->n > 2048) return fail(AQ_EUNSUPPORTED, "aq_set_missing: the missing-response kernel covers n <= 2048");
     if (!c->xraw) return fail(AQ_ESTATE, "aq_set_missing after aq_release_x");
+    if (c->has_mis) return fail(AQ_ESTATE, "aq_set_missing: the missing-value pattern of a context is set once");
     AQ_CUDA(cudaSetDevice(c->device));
     const size_t pq = (size_t)c->p_pad * c->q_pad;
+    // Two kernels serve coreDualMisLoop: the tile-structured one (the blocked tensor-core sweep with masked accumulators
+    // and a per-trait Gram band table of 128 B per SNP x trait pair, n <= 5376) and the warp-per-trait one (no table,
+    // n <= 2048, ~8x slower).  The tile path is taken whenever its table fits beside the rest; AQ_MIS_KERNEL=warp|tile forces.
+    const char* force = std::getenv("AQ_MIS_KERNEL");
+    const bool want_warp = force && std::strcmp(force, "warp") == 0, want_tile = force && std::strcmp(force, "tile") == 0;
+    CfgInfo cfgm;
+    bool tile_ok = !want_warp && pick_cfg_mis(c->n, &cfgm);
+    if (tile_ok) {
+        size_t fr = 0, tot = 0;
+        AQ_CUDA(cudaMemGetInfo(&fr, &tot));
+        const size_t ntiles16 = (size_t)(c->q + 15) / 16;
+        const double need = 8.0 * (double)ntiles16 * c->nb * 128 * 16 + 3.0 * 8.0 * (double)pq +
+                            8.0 * (double)c->nb * cfgm.ncta * (double)cfgm.tile_doubles +
+                            16.0 * (double)c->q_pad * cfgm.n_pad * cfgm.ncta + (double)((size_t)256 << 20);
+        const double freed = 8.0 * (double)c->nb * c->cfg.ncta * (double)c->cfg.tile_doubles + 16.0 * (double)c->q_pad * c->ld_resid;
+        if (need > (double)fr + freed) tile_ok = false;
+    }
+    if (tile_ok) return set_missing_tile(c, cfgm, mis_pat, n_obs);
+    if (want_tile) return fail(AQ_EUNSUPPORTED, "aq_set_missing: the tile-structured kernel needs n <= 5376 and 128 B per SNP x trait pair");
+    if (c->n > 2048)
+        return fail(AQ_EUNSUPPORTED, "aq_set_missing: no room for the tile kernel's Gram band table (128 B per SNP x trait pair) "
+                                     "and the warp-per-trait kernel covers n <= 2048 only");
     if (!c->mask) AQ_CUDA(cudaMalloc((void**)&c->mask, sizeof(unsigned long long) * 32 * (size_t)c->q_pad));
     if (!c->xnsq) AQ_CUDA(cudaMalloc((void**)&c->xnsq, sizeof(double) * pq));
     if (!c->n_obs) AQ_CUDA(cudaMalloc((void**)&c->n_obs, sizeof(double) * c->q_pad));
@@ -1201,7 +1401,7 @@ int aq_set_state_mis(aq_ctx* c, const double* gam_vb, const double* mu_beta_vb, 
     if (rc != AQ_OK) return rc;
     AQ_CUDA(cudaMemcpyAsync(c->resid, c->ymat, sizeof(double) * (size_t)c->q_pad * c->ld_resid, cudaMemcpyDeviceToDevice,
                             c->stream));
-    rc = launch_mis(c, /*mode=*/1, 1.0, 0.0, 0.0);
+    rc = c->mis_tile ? launch_sweep(c, /*mode=*/1, 1.0, 0.0) : launch_mis(c, /*mode=*/1, 1.0, 0.0, 0.0);
     if (rc != AQ_OK) return rc;
     c->have_state = true;
     const int rows[7] = {kMisGam, kMisGamMu2, kMisS2Gam, kMisRsq, kMisXnS2Gam, kMisXnGamMu2, kMisXnBeta2};
@@ -1221,7 +1421,17 @@ int aq_sweep_mis(aq_ctx* c, double cc, double log_sig2_inv_vb, double sig2_inv_v
     AQ_CUDA(cudaSetDevice(c->device));
     AQ_CUDA(cudaMemcpyAsync(c->tvec, tau_vb, sizeof(double) * c->q, cudaMemcpyHostToDevice, c->stream));
     AQ_CUDA(cudaMemcpyAsync(c->tvec + c->q_pad, log_tau_vb, sizeof(double) * c->q, cudaMemcpyHostToDevice, c->stream));
-    int rc = launch_mis(c, /*mode=*/0, cc, log_sig2_inv_vb, sig2_inv_vb);
+    int rc;
+    if (c->mis_tile) {
+        // sig2_beta_vb(j, k) of this sweep, as a = c sig2_beta tau and log sig2_beta (one streaming pass, 24 B per pair)
+        mis_prep_kernel<<<dim3((c->q + 255) / 256, std::min(c->p, 4096)), 256, 0, c->stream>>>(
+            c->xnsq, c->sig2tab, c->tvec, c->p, c->q, c->q_pad, cc, sig2_inv_vb, c->atab, c->ltab);
+        AQ_CUDA(cudaGetLastError());
+        c->launches++;
+        rc = launch_sweep(c, /*mode=*/0, cc, log_sig2_inv_vb);
+    } else {
+        rc = launch_mis(c, /*mode=*/0, cc, log_sig2_inv_vb, sig2_inv_vb);
+    }
     if (rc != AQ_OK) return rc;
     const int rows[9] = {kMisGam, kMisGamMu2, kMisS2Gam, kMisXnGamMu2, kMisXnS2Gam, kMisXnBeta2, kMisRsq, kMisZ, kMisGamLogS2};
     double* outs[9] = {colsum_gam, colsum_gam_mu2, colsum_sig2b_gam, colsum_xn_gam_mu2, colsum_xn_sig2b_gam,

@@ -227,4 +227,106 @@ __global__ void pack_mask_kernel(const double* __restrict__ mis, int n, int q, i
     if (lane == 0) n_obs[k] = cnt;
 }
 
+// ---------------------------------------------------------------- tile-structured missing-response path (aq_sweep.cuh, MIS)
+// mis: [q][n] doubles as above.  Bit matrix for the MMA warps' accumulator masks: bit i of word i / 64 of row k = sample i of
+// trait k is observed (rows of padding traits and bits of padding samples stay 0); zeroes Y where missing; counts.
+__global__ void pack_bits_kernel(const double* __restrict__ mis, int n, int q, int mwords, int ld,
+                                 unsigned long long* __restrict__ mbits, double* __restrict__ ymat, double* __restrict__ n_obs) {
+    const int lane = threadIdx.x & 31;
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k >= q) return;
+    double cnt = 0.0;
+    for (int w = lane; w < mwords; w += 32) {
+        unsigned long long bits = 0ull;
+        for (int b = 0; b < 64; ++b) {
+            const int i = w * 64 + b;
+            if (i < n) {
+                if (mis[(size_t)k * n + i] != 0.0) { bits |= 1ull << b; cnt += 1.0; }
+                else ymat[(size_t)k * ld + i] = 0.0;
+            }
+        }
+        mbits[(size_t)k * mwords + w] = bits;
+    }
+    cnt = warp_sum(cnt);
+    if (lane == 0) n_obs[k] = cnt;
+}
+
+// Per-trait Gram band of every (SNP block, 16-trait tile):  gk[tile][b][t * 16 + u][kk] = G[t][u] - sum over the MISSING
+// samples i of trait kk of x_it x_iu  =  (X' diag(mis_k) X)[t][u]  (the reference's cp_X - cp_X_rm[[k]],
+// R/atlasqtl_global_local_core.R:25-32, restricted to the band the blocked sweep needs: u = 0..7 the NEXT block's SNPs,
+// u = 8..15 this block's).  G comes from the tile image's band; the missing samples of a trait from its CSR list.
+// Its diagonal is X_norm_sq(j, k) = crossprod(X^2, mis_pat) (:23), written out on the way.
+// Grid (nb, tiles), 128 threads = one (t, u) pair each, 16 traits in registers.  Once per order, not per sweep.
+__global__ void __launch_bounds__(128) gk_build_kernel(const double* __restrict__ tiles, int nb, int nslice, int n_pad_c, int xs,
+                                                       size_t tile_stride, const int* __restrict__ mis_off,
+                                                       const int* __restrict__ mis_idx, int q, int q_pad,
+                                                       double* __restrict__ gk, double* __restrict__ xnsq) {
+    const int b = blockIdx.x, tile = blockIdx.y;
+    const int t = threadIdx.x >> 4, u = threadIdx.x & 15;
+    const int uu = u & 7;
+    const bool next = u < 8;
+    const bool have = !next || b + 1 < nb;
+    const int bu = next ? b + 1 : b;
+    const double g0 = tiles[((size_t)b * nslice) * tile_stride + (size_t)kBlk * xs + t * 16 + u];   // (every slice carries the band)
+    double acc[16];
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+        const int k = tile * 16 + kk;
+        double a = g0;
+        if (have && k < q) {
+            const int i0 = mis_off[k], i1 = mis_off[k + 1];
+            double sub = 0.0;
+            for (int ii = i0; ii < i1; ++ii) {
+                const int i = mis_idx[ii];
+                const int r = i / n_pad_c, li = i - r * n_pad_c;
+                const double xt = tiles[((size_t)b * nslice + r) * tile_stride + (size_t)t * xs + swz(li, t)];
+                const double xu = tiles[((size_t)bu * nslice + r) * tile_stride + (size_t)uu * xs + swz(li, uu)];
+                sub = fma(xt, xu, sub);
+            }
+            a -= sub;
+        }
+        acc[kk] = a;
+    }
+    double* dst = gk + (((size_t)tile * nb + b) * 128 + threadIdx.x) * 16;
+#pragma unroll
+    for (int kk = 0; kk < 16; kk += 2) {
+        double2 v;
+        v.x = acc[kk];
+        v.y = acc[kk + 1];
+        *reinterpret_cast<double2*>(dst + kk) = v;
+    }
+    if (u == 8 + t) {   // diagonal: X_norm_sq(j, k) for the SNP in slot t
+        const int j = reinterpret_cast<const int*>(tiles + ((size_t)b * nslice) * tile_stride + (size_t)kBlk * xs + 128)[t];
+        if (j >= 0) {
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk)
+                if (tile * 16 + kk < q_pad) xnsq[(size_t)j * q_pad + tile * 16 + kk] = acc[kk];
+        }
+    }
+}
+
+// Per-sweep p x q tables of the tile path: a = c sig2_beta tau = 1 / (X_norm_sq + sig2_inv) and log sig2_beta_vb(j, k) with
+// sig2_beta_vb = a / (c tau_k) (update_sig2_beta_vb_, R/update_vb.R:47) -- or, when the caller hands sig2_beta_vb over
+// (stateless coreDualMisLoop entry), a = c sig2_beta tau from it.  HBM bound, 24 B per pair.
+__global__ void mis_prep_kernel(const double* __restrict__ xnsq, const double* __restrict__ sig2tab,
+                                const double* __restrict__ tau, int p, int q, int q_pad, double c, double sig2_inv,
+                                double* __restrict__ atab, double* __restrict__ ltab) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= q) return;
+    const double ctau = c * tau[k];
+    for (int j = blockIdx.y; j < p; j += gridDim.y) {
+        const size_t off = (size_t)j * q_pad + k;
+        double a, s2;
+        if (sig2tab) {
+            s2 = sig2tab[off];
+            a = s2 * ctau;
+        } else {
+            a = 1.0 / (xnsq[off] + sig2_inv);
+            s2 = a / ctau;
+        }
+        atab[off] = a;
+        ltab[off] = log(s2);
+    }
+}
+
 }  // namespace aq

@@ -26,6 +26,7 @@
 // the correction is accumulated inside the chain of block b (independent FMAs that fill its latency bubbles).
 #pragma once
 #include "aq_common.cuh"
+#include "aq_mis.cuh"
 #ifdef AQ_TIMING
 // development only: per-section cycle sums of the chain (0-3) and helper (4-9) warps of CTA 0, kept in registers and
 // written once at the end (a global read-modify-write per probe would put an L2 round trip into every section)
@@ -87,13 +88,25 @@ struct SweepParams {
     int nseg;
     int seg_len;
     int* seg_done;          // [ntiles] segments completed per tile, zeroed before the launch (NULL iff nseg == 1)
+    // Missing-response variant (SweepCfg<..., MIS = true>; coreDualMisLoop, src/coreLoop.cpp:91-138): every trait has its own
+    // Gram matrix X' diag(mis_k) X.  The residual tile is kept MASKED (zero in the missing rows of its trait), so
+    // S = X_b' R needs no mask; the in-block / look-ahead Gram entries come from a per-trait band precomputed once per
+    // order (gk), and sig2_beta_vb(j, k) = 1 / (c (X_norm_sq(j, k) + sig2_inv) tau_k) enters through two p x q tables.
+    const unsigned long long* mbits;  // [q_pad][mwords] bit i of row k: sample i of trait k is observed
+    int mwords;
+    const double* xnsq;     // [p_pad][q_pad] X_norm_sq = crossprod(X^2, mis_pat) (R/atlasqtl_global_local_core.R:23)
+    const double* atab;     // [p_pad][q_pad] a = c sig2_beta tau = 1 / (X_norm_sq + sig2_inv)          (src/coreLoop.cpp:125)
+    const double* ltab;     // [p_pad][q_pad] log sig2_beta_vb(j, k)                                     (:129)
+    const double* gk;       // [tile][nb][128][16] per-trait Gram band, entry t * 16 + u as in the tile image's band
+    double* mis_out;        // [kMisOutputs][q_pad] per-trait sums of the missing-response path
     long long* timing;      // development only (-DAQ_TIMING): per-section cycle sums of the chain warp
 };
 
 constexpr int kMaxCluster = 8;
 
-template <int MT_, int NT_, bool CL_ = false>
+template <int MT_, int NT_, bool CL_ = false, bool MIS_ = false>
 struct SweepCfg {
+    static constexpr bool kMis = MIS_;  // missing-response variant
     static constexpr int WS = 14;   // MMA warps, all along samples (split-K of the S GEMM)
     static constexpr int MT = MT_;  // 8-trait M tiles per MMA warp
     static constexpr int NT = NT_;  // 8-sample N tiles per MMA warp
@@ -121,8 +134,13 @@ struct SweepCfg {
     static constexpr size_t kSsumDoubles = kChainSums ? 0 : (size_t)2 * kT * kSps;  // [2][kT][kSps] summed S tile for the chain
     static constexpr size_t kDbufDoubles = (size_t)2 * kT * kBlk;
     static constexpr size_t kRsqDoubles = (size_t)WS * kT;
-    static constexpr size_t kIoDoubles = (size_t)2 * kBlk * 2 * kT;  // [2][kBlk][2][kT]: in beta_old, c (D + cst); out gam, mu
-    static constexpr size_t kStgDoubles = (size_t)5 * kBlk * kT;     // [5][kBlk][kT]: gam, mu, D, W, I0 rows of the next block
+    // [2][kBlk][kIoPer][kT]: in beta_old, c (D + cst) (+ a, bq per pair with missing responses); out gam, mu
+    static constexpr int kIoPer = kMis ? 4 : 2;
+    static constexpr size_t kIoDoubles = (size_t)2 * kBlk * kIoPer * kT;
+    // [kStgArrays][kBlk][kT]: gam, mu, D, W, I0 (+ X_norm_sq, a, log sig2_beta) rows of the next block
+    static constexpr int kStgArrays = kMis ? 8 : 5;
+    static constexpr size_t kStgDoubles = (size_t)kStgArrays * kBlk * kT;
+    static constexpr size_t kGkDoubles = kMis ? (size_t)2 * 128 * kT : 0;   // [2][128][kT] per-trait Gram band of a block
     static constexpr uint32_t kDeltaBytes = (uint32_t)(kT * kBlk * sizeof(double));  // one -Delta block
     // cluster variant only: followers' reduced S tiles and squared-norm partials land in the leader's shared memory
     static constexpr size_t kRedDoubles = kCl ? (size_t)2 * (kMaxCluster - 1) * kT * kSps : 0;
@@ -130,11 +148,12 @@ struct SweepCfg {
     // full, empty, dready, dcons, sred, rsqbar, inready, sfree, sdone [2][4]
     static constexpr int kNumBars = 2 * kStages + 2 + 2 + 2 + 1 + 2 + 1 + 8;
     static constexpr size_t kSmemBytes = (kStages * kTileDoubles + kSpartDoubles + kSsumDoubles + kDbufDoubles + kRsqDoubles +
-                                          kIoDoubles + kStgDoubles + kRedDoubles + kRsqAllDoubles) *
+                                          kIoDoubles + kStgDoubles + kRedDoubles + kRsqAllDoubles + kGkDoubles) *
                                              sizeof(double) +
                                          24 * sizeof(uint64_t);
     static_assert(kNumBars <= 24, "barrier block");
     static_assert(kT <= 32, "one chain lane per trait");
+    static_assert(!kMis || kT == 16, "the missing-response variant uses 16-trait tiles (its Gram band table is laid out for them)");
     static_assert(kXS % 16 == 8, "row stride must be 8 mod 16 doubles");
     static_assert(kSmemBytes <= 232448, "shared memory budget (227 KB)");
 };
@@ -280,6 +299,8 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
     constexpr int WS = Cfg::WS, MT = Cfg::MT, NT = Cfg::NT, kT = Cfg::kT, XS = Cfg::kXS;
     constexpr int kStages = Cfg::kStages;
     constexpr bool kCl = Cfg::kCl;
+    constexpr bool kMis = Cfg::kMis;
+    constexpr int kIoPer = Cfg::kIoPer;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* tiles = reinterpret_cast<double*>(smem_raw);
     double* spart = tiles + kStages * Cfg::kTileDoubles;  // [WS][kT][kSps]
@@ -290,7 +311,8 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
     double* stg = iobuf + Cfg::kIoDoubles;                // [5][kBlk][kT]
     double* red = stg + Cfg::kStgDoubles;                 // leader: [2][kMaxCluster-1][kT][kSps]
     double* rsq_all = red + Cfg::kRedDoubles;             // leader: [kMaxCluster-1][kT]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(rsq_all + Cfg::kRsqAllDoubles);
+    double* gkbuf = rsq_all + Cfg::kRsqAllDoubles;        // missing responses: [2][128][kT] per-trait Gram band
+    uint64_t* bars = reinterpret_cast<uint64_t*>(gkbuf + Cfg::kGkDoubles);
     uint64_t* full = bars;                       // [kStages]  tile landed (tx bytes)
     uint64_t* empty = bars + kStages;            // [kStages]  MMA warps released the tile
     uint64_t* dready = bars + 2 * kStages;       // [2]  chain warp published -Delta (in every CTA of the cluster)
@@ -406,6 +428,23 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
             // the AQ_S_FINISH_AT experiment moves it into the rank-8 update of the previous block).
             constexpr int kSC = (MT >= 4) ? 1 : 2;   // accumulator chains per M tile
             double sa[MT][2][2];
+            // missing responses: bit 2 nt + e of mb[mt] = this lane's accumulator element (mt, nt, e) belongs to an observed sample
+            uint32_t mb[MT];
+            if constexpr (kMis) {
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const unsigned long long* row = P.mbits + (size_t)(k0 + tr0 + mt * 8 + g) * P.mwords;
+                    uint32_t bits = 0;
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int smp = ig + nt * 8 + 2 * l + e;
+                            bits |= (uint32_t)((__ldg(row + (smp >> 6)) >> (smp & 63)) & 1ull) << (2 * nt + e);
+                        }
+                    mb[mt] = bits;
+                }
+            }
             auto s_issue = [&](long gbi) {
                 const int stage = (int)(gbi % kStages);
                 AQ_T0();
@@ -508,6 +547,16 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     if (nt == Cfg::kSFin && s_next) s_finish(gb + 1);   // the S accumulators have drained meanwhile
                 }
                 if (Cfg::kSFin >= NT && s_next) s_finish(gb + 1);
+                if constexpr (kMis) {
+                    // keep the residual masked: r_k -= delta (mis_k o x_j)  (src/coreLoop.cpp:132 in sample space)
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) {
+                            if (!((mb[mt] >> (2 * nt)) & 1u)) acc[mt][nt][0] = 0.0;
+                            if (!((mb[mt] >> (2 * nt + 1)) & 1u)) acc[mt][nt][1] = 0.0;
+                        }
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[stage]);
                 AQ_T(15);
@@ -628,16 +677,22 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 const int tile = un.tile;
                 const int k = P.k_base + tile * kT + tls;
                 const bool valid = active && k < P.q;
-                const double sig2 = P.sig2_beta[k];
-                const double cst = -(P.log_tau[k] + P.log_sig2_inv + log(sig2)) / 2;  // src/coreLoop.cpp:56
+                // src/coreLoop.cpp:56; with missing responses :108 (log sig2_beta_vb(j, k) enters per pair, :129)
+                double cst;
+                if constexpr (kMis) cst = -(P.log_tau[k] + P.log_sig2_inv) / 2;
+                else cst = -(P.log_tau[k] + P.log_sig2_inv + log(P.sig2_beta[k])) / 2;
+                const double ctau = P.c * P.tau[k], inv_ctau = 1.0 / ctau;   // (missing responses) sig2_beta = a / (c tau)
                 double sg = 0.0, sgm2 = 0.0, sb2 = 0.0, sz = 0.0;
+                double ss2g = 0.0, sxgm2 = 0.0, sxs2g = 0.0, sxb2 = 0.0, sgl = 0.0;   // missing-response sums (aq_mis.cuh)
+                double xnn[kTP], s2n[kTP], lsn[kTP];   // X_norm_sq, sig2_beta, log sig2_beta of the block being prepared
                 double* rowrow = P.rowpart ? P.rowpart + (size_t)(P.rowpart_base + tile) * P.p_pad : nullptr;
                 // asynchronous copies (LDGSTS) of this lane's gam / mu / D / W / I0 elements of block `blk` into the staging
                 // buffer: issued a whole block ahead, so neither preparing a block nor finishing it ever waits on HBM or L2
                 auto stage_rows = [&](int blk) {
                     // 16-byte copies: a row of kT traits is kT / 2 lanes wide, so one instruction covers 64 / kT rows
                     constexpr int kLanesPerRow = kT / 2, kRowsPerInst = 32 / kLanesPerRow;
-                    constexpr int kArrays = kStageWI ? 5 : 3;
+                    constexpr int kArrays = kMis ? 8 : (kStageWI ? 5 : 3);
+                    static_assert(!kMis || kStageWI, "the missing-response variant stages all its rows");
                     const int idr = __ldg(P.order + (size_t)blk * kBlk + (lane & 7));
                     const int rsub = lane / kLanesPerRow, csub = 2 * (lane % kLanesPerRow);
                     const size_t kcol = (size_t)P.k_base + (size_t)tile * kT + csub;
@@ -647,15 +702,25 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                         const int a = row / kBlk, t = row % kBlk;
                         const int idt = __shfl_sync(0xffffffffu, idr, t);
                         if (row < kArrays * kBlk) {
-                            const double* base = a == 0 ? P.gam : a == 1 ? P.mu : a == 2 ? P.dtab : a == 3 ? P.wtab : P.i0tab;
+                            const double* base = a == 0 ? P.gam : a == 1 ? P.mu : a == 2 ? P.dtab : a == 3 ? P.wtab :
+                                                 a == 4 ? P.i0tab : a == 5 ? P.xnsq : a == 6 ? P.atab : P.ltab;
                             cp_async16(stg + (size_t)row * kT + csub, base + (size_t)(idt < 0 ? 0 : idt) * P.q_pad + kcol);
                         }
                     }
                     cp_async_commit();
                 };
+                // missing responses: the per-trait Gram band of block `blk` (16 KB) -> buffer g & 1, 32 copies per lane
+                auto stage_gk = [&](long g, int blk) {
+                    if constexpr (kMis) {
+                        const double* src = P.gk + (((size_t)(P.k_base / kT + tile) * P.nb + blk) * 128) * kT;
+                        double* dst = gkbuf + (size_t)(g & 1) * 128 * kT;
+                        for (int i = lane; i < 128 * kT / 2; i += 32) cp_async16(dst + 2 * i, src + 2 * i);
+                        cp_async_commit();
+                    }
+                };
                 auto pre = [&](long g, int blk) {
                     AQ_T0();
-                    double* io = iobuf + (size_t)(g & 1) * kBlk * 2 * kT;
+                    double* io = iobuf + (size_t)(g & 1) * kBlk * kIoPer * kT;
                     cp_async_wait_all();  // issued a whole block earlier
                     __syncwarp();         // (each lane waited for its own copies; the rows are read by other lanes)
 #pragma unroll
@@ -668,9 +733,21 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                             wn[i] = stg[(3 * kBlk + t) * kT + tls];
                             in[i] = stg[(4 * kBlk + t) * kT + tls];
                         }
-                        if (active) {
-                            io[(t * 2 + 0) * kT + tl] = idn[i] >= 0 ? go * mo : 0.0;  // beta_old (0 for padding slots)
-                            io[(t * 2 + 1) * kT + tl] = P.c * (dd + cst);              // :75-77 without the mu^2 term
+                        if constexpr (kMis) {
+                            const double xn = stg[(5 * kBlk + t) * kT + tls], aa = stg[(6 * kBlk + t) * kT + tls];
+                            const double ls = stg[(7 * kBlk + t) * kT + tls];
+                            xnn[i] = xn;
+                            s2n[i] = aa * inv_ctau;        // sig2_beta_vb(j, k), update_sig2_beta_vb_ R/update_vb.R:47
+                            lsn[i] = ls;
+                            if (active) {
+                                io[(t * kIoPer + 0) * kT + tl] = idn[i] >= 0 ? go * mo : 0.0;
+                                io[(t * kIoPer + 1) * kT + tl] = P.c * (dd - 0.5 * ls + cst);   // :127-129 without the mu^2 term
+                                io[(t * kIoPer + 2) * kT + tl] = aa;                            // mu = a s              (:125)
+                                io[(t * kIoPer + 3) * kT + tl] = 0.5 * P.c * aa * ctau;         // c mu^2 / (2 sig2_beta) = bq s^2
+                            }
+                        } else if (active) {
+                            io[(t * kIoPer + 0) * kT + tl] = idn[i] >= 0 ? go * mo : 0.0;  // beta_old (0 for padding slots)
+                            io[(t * kIoPer + 1) * kT + tl] = P.c * (dd + cst);              // :75-77 without the mu^2 term
                         }
                     }
                     if (blk + 1 < un.b1) stage_rows(blk + 1);
@@ -692,17 +769,19 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     if (lane == 0) mbar_arrive(&inready[g & 1]);
                     AQ_T(7);
                 };
-                auto post = [&](long g, const double (&ww)[kTP], const double (&ii)[kTP]) {
+                auto post = [&](long g, int blk, const double (&ww)[kTP], const double (&ii)[kTP], const double (&xc)[kTP],
+                                const double (&s2c)[kTP], const double (&lsc)[kTP]) {
                     AQ_T0();
                     mbar_wait(&dready[g & 1], (uint32_t)((g >> 1) & 1));
                     AQ_T(8);
-                    const double* io = iobuf + (size_t)(g & 1) * kBlk * 2 * kT;
+                    if (blk + 2 < un.b1) stage_gk(g + 2, blk + 2);   // the chain is through with buffer g & 1
+                    const double* io = iobuf + (size_t)(g & 1) * kBlk * kIoPer * kT;
                     double zrow[kTP];
 #pragma unroll
                     for (int i = 0; i < kTP; ++i) {
                         const int t = t0 + i;
-                        const double gm = io[(t * 2 + 0) * kT + tls];
-                        const double m = io[(t * 2 + 1) * kT + tls];
+                        const double gm = io[(t * kIoPer + 0) * kT + tls];
+                        const double m = io[(t * kIoPer + 1) * kT + tls];
                         zrow[i] = 0.0;
                         if (idc[i] >= 0) {
                             const double bn = gm * m;  // :79
@@ -711,6 +790,13 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                             sgm2 = fma(bn, m, sgm2);
                             sb2 = fma(bn, bn, sb2);
                             sz += z;
+                            if constexpr (kMis) {
+                                ss2g = fma(s2c[i], gm, ss2g);
+                                sxgm2 = fma(xc[i] * bn, m, sxgm2);
+                                sxs2g = fma(xc[i] * s2c[i], gm, sxs2g);
+                                sxb2 = fma(xc[i] * bn, bn, sxb2);
+                                sgl = fma(gm, lsc[i], sgl);
+                            }
                             if (valid) {
                                 const size_t off = (size_t)idc[i] * P.q_pad + k;
                                 P.gam[off] = gm;
@@ -732,13 +818,18 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     }
                     AQ_T(9);
                 };
+                stage_gk(gb, un.b0);
+                if (un.b0 + 1 < un.b1) stage_gk(gb + 1, un.b0 + 1);
                 stage_rows(un.b0);
                 pre(gb, un.b0);
                 for (int b = un.b0; b < un.b1; ++b, ++gb) {
-                    double ww[kTP], ii[kTP];
+                    double ww[kTP], ii[kTP], xc[kTP], s2c[kTP], lsc[kTP];
 #pragma unroll
                     for (int i = 0; i < kTP; ++i) {
                         idc[i] = idn[i];
+                        xc[i] = xnn[i];
+                        s2c[i] = s2n[i];
+                        lsc[i] = lsn[i];
                         if (kStageWI) {
                             ww[i] = wn[i];
                             ii[i] = in[i];
@@ -749,16 +840,35 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                         }
                     }
                     if (b + 1 < un.b1) pre(gb + 1, b + 1);
-                    post(gb, ww, ii);
+                    post(gb, b, ww, ii, xc, s2c, lsc);
                 }
                 if (kH == 2) {
                     sg += __shfl_xor_sync(0xffffffffu, sg, 16);
                     sgm2 += __shfl_xor_sync(0xffffffffu, sgm2, 16);
                     sb2 += __shfl_xor_sync(0xffffffffu, sb2, 16);
                     sz += __shfl_xor_sync(0xffffffffu, sz, 16);
+                    if constexpr (kMis) {
+                        ss2g += __shfl_xor_sync(0xffffffffu, ss2g, 16);
+                        sxgm2 += __shfl_xor_sync(0xffffffffu, sxgm2, 16);
+                        sxs2g += __shfl_xor_sync(0xffffffffu, sxs2g, 16);
+                        sxb2 += __shfl_xor_sync(0xffffffffu, sxb2, 16);
+                        sgl += __shfl_xor_sync(0xffffffffu, sgl, 16);
+                    }
                 }
                 unit_acquire(P, un, lane);   // the column sums of the earlier segments (fixed order: deterministic)
-                if (valid && half == 0) {
+                if constexpr (kMis) {   // (never segmented: one unit per tile)
+                    if (valid && half == 0) {
+                        double* o = P.mis_out + k;
+                        o[(size_t)kMisGam * P.q_pad] = sg;
+                        o[(size_t)kMisGamMu2 * P.q_pad] = sgm2;
+                        o[(size_t)kMisS2Gam * P.q_pad] = ss2g;
+                        o[(size_t)kMisXnGamMu2 * P.q_pad] = sxgm2;
+                        o[(size_t)kMisXnS2Gam * P.q_pad] = sxs2g;
+                        o[(size_t)kMisXnBeta2 * P.q_pad] = sxb2;
+                        o[(size_t)kMisZ * P.q_pad] = sz;
+                        o[(size_t)kMisGamLogS2 * P.q_pad] = sgl;
+                    }
+                } else if (valid && half == 0) {
                     if (un.seg > 0) {
                         sg += __ldcg(P.cs_gam + k);
                         sgm2 += __ldcg(P.cs_gmu2 + k);
@@ -805,9 +915,12 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
             const bool valid = active && k < P.q;
             if (P.mode == 0) {
                 // ---- sweep: only the serial recurrence lives here; inputs arrive through shared memory (helper warp)
-                const double sig2 = P.sig2_beta[k];
-                const double a = P.c * sig2 * P.tau[k];             // src/coreLoop.cpp:73:  mu = a * s
-                const double bq = P.c * a * a / (2.0 * sig2);       // :76  c * mu^2 / (2 sig2_beta) = bq * s^2
+                double a = 0.0, bq = 0.0;   // (missing responses: per pair, through shared memory with the other inputs)
+                if constexpr (!kMis) {
+                    const double sig2 = P.sig2_beta[k];
+                    a = P.c * sig2 * P.tau[k];                      // src/coreLoop.cpp:73:  mu = a * s
+                    bq = P.c * a * a / (2.0 * sig2);                // :76  c * mu^2 / (2 sig2_beta) = bq * s^2
+                }
                 double corr[kBlk];  // look-ahead correction of the NEXT block, accumulated while this one is resolved
 #pragma unroll
                 for (int t = 0; t < kBlk; ++t) corr[t] = 0.0;
@@ -815,14 +928,22 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     AQ_T0();
                     const int stage = (int)(gb % kStages);
                     mbar_wait(&full[stage], (uint32_t)((gb / kStages) & 1));
-                    const double* gband = tiles + stage * Cfg::kTileDoubles + kBlk * XS;
+                    // Gram band of the block, entry (t, u) at gband[(t * 16 + u) * gstride]: the tile image's band, shared by
+                    // all traits -- or, with missing responses, this lane's column of the per-trait band the helper fetched
+                    const double* gband = kMis ? gkbuf + (size_t)(gb & 1) * 128 * kT + tsum
+                                               : tiles + stage * Cfg::kTileDoubles + kBlk * XS;
+                    constexpr int gstride = kMis ? kT : 1;
                     mbar_wait(&inready[gb & 1], (uint32_t)((gb >> 1) & 1));   // beta_old, c (D + cst): staged a block ahead
-                    double* io = iobuf + (size_t)(gb & 1) * kBlk * 2 * kT;
-                    double s[kBlk], bo[kBlk], ap[kBlk], nd[kBlk];
+                    double* io = iobuf + (size_t)(gb & 1) * kBlk * kIoPer * kT;
+                    double s[kBlk], bo[kBlk], ap[kBlk], nd[kBlk], av[kMis ? kBlk : 1], bv[kMis ? kBlk : 1];
 #pragma unroll
                     for (int t = 0; t < kBlk; ++t) {
-                        bo[t] = io[(t * 2 + 0) * kT + tsum];
-                        ap[t] = io[(t * 2 + 1) * kT + tsum];
+                        bo[t] = io[(t * kIoPer + 0) * kT + tsum];
+                        ap[t] = io[(t * kIoPer + 1) * kT + tsum];
+                        if constexpr (kMis) {
+                            av[t] = io[(t * kIoPer + 2) * kT + tsum];
+                            bv[t] = io[(t * kIoPer + 3) * kT + tsum];
+                        }
                     }
                     if (Cfg::kChainSums) {
                         // S = X_b' R: this warp sums the split-K partials itself the moment the MMA warps have delivered
@@ -842,26 +963,26 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
 #pragma unroll
                     for (int t = 0; t < kBlk; ++t) {
                         // S was formed before the previous block's update was applied (corr); leave-one-out: + beta_old |X_t|^2
-                        s[t] = fma(bo[t], gband[t * 16 + 8 + t], s[t] + corr[t]);
+                        s[t] = fma(bo[t], gband[(t * 16 + 8 + t) * gstride], s[t] + corr[t]);
                         corr[t] = 0.0;
                     }
                     AQ_T(1);
 #pragma unroll
                     for (int t = 0; t < kBlk; ++t) {
                         const double st = s[t];
-                        const double m = a * st;                             // :73
-                        const double x = fma(st * st, -bq, ap[t]);           // :75-77
+                        const double m = (kMis ? av[kMis ? t : 0] : a) * st;                        // :73  (:125)
+                        const double x = fma(st * st, -(kMis ? bv[kMis ? t : 0] : bq), ap[t]);      // :75-77  (:127-129)
                         const double gm = logistic_neg(x);                   // 1/(1+e^x) == exp(-log1pexp(x))
                         const double dlt = fma(gm, m, -bo[t]);               // :79 beta_new - beta_old (0 for padding slots)
-                        const double* grow = gband + t * 16;                 // row t: [next block | this block]
+                        const double* grow = gband + t * 16 * gstride;       // row t: [next block | this block]
 #pragma unroll
-                        for (int u = t + 1; u < kBlk; ++u) s[u] = fma(-grow[8 + u], dlt, s[u]);
+                        for (int u = t + 1; u < kBlk; ++u) s[u] = fma(-grow[(8 + u) * gstride], dlt, s[u]);
 #pragma unroll
-                        for (int u = 0; u < kBlk; ++u) corr[u] = fma(-grow[u], dlt, corr[u]);
+                        for (int u = 0; u < kBlk; ++u) corr[u] = fma(-grow[u * gstride], dlt, corr[u]);
                         nd[t] = -dlt;
                         if (active) {
-                            io[(t * 2 + 0) * kT + tl] = gm;
-                            io[(t * 2 + 1) * kT + tl] = m;
+                            io[(t * kIoPer + 0) * kT + tl] = gm;
+                            io[(t * kIoPer + 1) * kT + tl] = m;
                         }
                     }
                     AQ_T(2);
@@ -870,7 +991,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 }
             } else {
                 // ---- mode 1: R = Y - X beta from the loaded state, and its per-trait sums
-                double sg = 0.0, sgm2 = 0.0, sb2 = 0.0;
+                double sg = 0.0, sgm2 = 0.0, sb2 = 0.0, sxg = 0.0, sxgm2 = 0.0, sxb2 = 0.0;
                 for (int b = un.b0; b < un.b1; ++b, ++gb) {
                     const int stage = (int)(gb % kStages);
                     mbar_wait(&full[stage], (uint32_t)((gb / kStages) & 1));
@@ -886,6 +1007,12 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                             sg += go;
                             sgm2 = fma(bo, mo, sgm2);
                             sb2 = fma(bo, bo, sb2);
+                            if constexpr (kMis) {
+                                const double xn = P.xnsq[off];
+                                sxg = fma(xn, go, sxg);
+                                sxgm2 = fma(xn * bo, mo, sxgm2);
+                                sxb2 = fma(xn * bo, bo, sxb2);
+                            }
                         }
                         nd[t] = -bo;
                     }
@@ -896,7 +1023,17 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     publish(gb, nd);
                 }
                 unit_acquire(P, un, lane);
-                if (valid) {
+                if constexpr (kMis) {   // rows as mis_sweep_kernel's mode 1 leaves them (aq_mis.cuh)
+                    if (valid) {
+                        double* o = P.mis_out + k;
+                        o[(size_t)kMisGam * P.q_pad] = sg;
+                        o[(size_t)kMisGamMu2 * P.q_pad] = sgm2;
+                        o[(size_t)kMisS2Gam * P.q_pad] = sb2;
+                        o[(size_t)kMisXnGamMu2 * P.q_pad] = sxgm2;
+                        o[(size_t)kMisXnS2Gam * P.q_pad] = sxg;
+                        o[(size_t)kMisXnBeta2 * P.q_pad] = sxb2;
+                    }
+                } else if (valid) {
                     if (un.seg > 0) {
                         sg += __ldcg(P.cs_gam + k);
                         sgm2 += __ldcg(P.cs_gmu2 + k);

@@ -8,16 +8,30 @@ from problems import make_problem, mis_inputs, sweep_inputs
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["tile", "warp"], autouse=True)
+def mis_kernel(request, monkeypatch):
+    """Both CUDA kernels behind aq_sweep_mis: the tile-structured one (blocked tensor-core sweep with masked accumulators and
+    a per-trait Gram band table; the default whenever the table fits) and the warp-per-trait one (no table, n <= 2048)."""
+    monkeypatch.setenv("AQ_MIS_KERNEL", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("n,p,q,c,shuffle", [
     (60, 40, 12, 0.7, True),       # dual-feasible: checked against the reference's coreDualMisLoop itself
     (100, 75, 20, 1.0, False),
     (130, 33, 9, 0.9, True),       # n, p, q off every 32 / 8 boundary
     (700, 50, 17, 1.0, True),      # 32 samples per lane
     (1500, 40, 11, 0.8, True),     # 64 samples per lane
+    (784, 27, 35, 0.9, True),      # tile kernel: the largest single-CTA configuration, three tiles
+    (2500, 30, 20, 1.0, True),     # beyond the warp kernel's n <= 2048: 4-CTA clusters
+    (3000, 21, 40, 0.7, False),    # 6-CTA clusters (the C3 sample size)
+    (5000, 17, 24, 1.0, True),     # 8-CTA clusters (the C5 sample size)
 ])
-def test_single_sweep_parity_missing(oracle_built, n, p, q, c, shuffle):
+def test_single_sweep_parity_missing(oracle_built, mis_kernel, n, p, q, c, shuffle):
     from atlasqtl_b200.device import SweepContext
     native = oracle_built
+    if mis_kernel == "warp" and n > 2048:
+        pytest.skip("the warp-per-trait kernel covers n <= 2048")
     X, Y, hyper, init = make_problem(n, p, q)
     p, q = X.shape[1], Y.shape[1]
     si = sweep_inputs(X, Y, init, c=c)
