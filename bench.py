@@ -306,6 +306,8 @@ def main():
     ap.add_argument("--config", default="C2")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--na-frac", type=float, default=0.0,
+                    help="fraction of missing responses (NaN in Y): times the coreDualMisLoop path instead of coreDualLoop")
     args = ap.parse_args()
     # stdout carries the ONE JSON line and nothing else: whatever libraries print there (NCCL's version banner, ...) is
     # sent to stderr by pointing fd 1 at fd 2 for the run; the line itself goes to the saved descriptor
@@ -330,6 +332,9 @@ def main():
                           f"first {W}+{K} VB iterations", "n": n, "p": p, "q": q,
               "l2": "inputs larger than L2 (p x q arrays stream from HBM every step)",
               "parallelism": f"traits sharded over {world} GPU(s), X replicated"}
+    if args.na_frac > 0:
+        config["workload"] += f"; {100 * args.na_frac:g} % of the responses missing at random (coreDualMisLoop path)"
+        config["na_frac"] = args.na_frac
 
     if args.impl == "reference":
         if rank != 0:
@@ -417,6 +422,14 @@ def main():
             marks["t1"] = time.perf_counter()
             launches["t1"] = ctx.launch_count()
 
+    if args.na_frac > 0:
+        if isinstance(X, dict):
+            raise SystemExit("--na-frac needs a dense-X config (C1, C2, C4)")
+        # the same entries whatever the sharding: drawn per global chunk of 64 traits
+        for c0 in range((k0 // 64) * 64, k1, 64):
+            m = np.random.default_rng([123, 13, c0]).uniform(size=(64, n)) < args.na_frac
+            lo, hi = max(c0, k0), min(c0 + 64, k1)
+            Y[:, lo - k0:hi - k0][m[lo - c0:hi - c0].T] = np.nan
     trace = []
     t_up = time.time()
     if isinstance(X, dict):
@@ -429,7 +442,7 @@ def main():
         if world > 1:
             X["packed"] = None   # (kept at N = 1 for the CPU baseline's sample)
     else:
-        ctx = SweepContext(X, Y, device=local_rank)
+        ctx = SweepContext(X, np.where(np.isnan(Y), 0.0, Y) if args.na_frac > 0 else Y, device=local_rank)
         Xarg = X
     log(f"[rank {rank}] context created in {time.time() - t_up:.1f} s")
     try:
@@ -484,7 +497,8 @@ def main():
                          "frac": achieved / FP64_PEAK_TFLOPS,
                          "traffic": traffic, "traffic_source": traffic_src,
                          "traffic_algorithmic": 56.0 * p * ql + 8.0 * n * p + 16.0 * n * ql,
-                         "kernel": "sweep_kernel (fp64 DMMA m8n8k4), one sweep of this rank's trait slab",
+                         "kernel": "sweep_kernel (fp64 DMMA m8n8k4), one sweep of this rank's trait slab"
+                                   + (" -- missing-response variant (masked accumulators, per-trait Gram band)" if args.na_frac > 0 else ""),
                          "ms": sweep_ms, "plan": plan,
                          "peak_source": "measured fp64 DMMA peak, tools/microbench/fp64_peaks.cu on this pool "
                                         "(MEASURED_PEAKS.json has no fp64 entry)",
@@ -494,7 +508,9 @@ def main():
             "clocks": clocks, "check": check,
             "per_step_ms": {"sweep": sweep_ms, "rowsums": rows_ms, "tables": tables_ms,
                             "host": {k: float(v) for k, v in zip(seg_keys, host_ms)}, "over_ranks": "max"}}
-    if world == 1 and not args.no_cpu_baseline:
+    if args.na_frac > 0:
+        line["cpu_baseline"] = {"skipped": "the CPU arm times coreDualLoop (no missing responses); see the default run"}
+    elif world == 1 and not args.no_cpu_baseline:
         try:
             from oracle import native
             native.build()
