@@ -57,10 +57,12 @@ def coreDualMisLoop(cp_X, cp_X_rm, cp_Y_X, gam_vb, log_Phi_theta_plus_zeta, log_
                                       ctypes.c_double(c)))
 
 
-def logistic_neg_device(x, device=0):
-    """1 / (1 + exp(x)) evaluated on the device by the sweep's own routine (aq_test_logistic): a test hook."""
+def logistic_neg_device(x, device=0, variant=0):
+    """1 / (1 + exp(x)) evaluated on the device by the sweep's own routine (aq_test_logistic): a test hook.
+    variant 0 / 1: the two versions of the routine the kernel configurations use."""
     lib = _lib.load()
     x = np.ascontiguousarray(x, dtype=np.float64)
     out = np.empty_like(x)
-    _lib.check(lib.aq_test_logistic(ctypes.c_int(device), _lib.dptr(x), _lib.dptr(out), ctypes.c_int(x.size)))
+    _lib.check(lib.aq_test_logistic(ctypes.c_int(device), ctypes.c_int(variant), _lib.dptr(x), _lib.dptr(out),
+                                    ctypes.c_int(x.size)))
     return out

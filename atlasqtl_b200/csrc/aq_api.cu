@@ -1534,14 +1534,14 @@ int aq_sweep_plan(const aq_ctx* c, int* traits_per_tile, int* ntiles, int* group
 }
 
 namespace {
-__global__ void test_logistic_kernel(const double* __restrict__ x, double* __restrict__ out, int n) {
+__global__ void test_logistic_kernel(const double* __restrict__ x, double* __restrict__ out, int n, int variant) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = aq::logistic_neg(x[i]);
+    if (i < n) out[i] = variant ? aq::logistic_neg<true>(x[i]) : aq::logistic_neg<false>(x[i]);
 }
 }  // namespace
 
-int aq_test_logistic(int device, const double* x, double* out, int n) {
-    if (!x || !out || n < 0) return fail(AQ_EINVAL, "aq_test_logistic: bad argument");
+int aq_test_logistic(int device, int variant, const double* x, double* out, int n) {
+    if (!x || !out || n < 0 || (variant != 0 && variant != 1)) return fail(AQ_EINVAL, "aq_test_logistic: bad argument");
     if (n == 0) return AQ_OK;
     int rc = aq_device_info(device, nullptr, nullptr, nullptr);
     if (rc != AQ_OK) return rc;
@@ -1550,7 +1550,7 @@ int aq_test_logistic(int device, const double* x, double* out, int n) {
     cudaError_t e = cudaMalloc((void**)&dout, sizeof(double) * (size_t)n);
     if (e == cudaSuccess) e = cudaMemcpy(dx, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
-        test_logistic_kernel<<<(n + 255) / 256, 256>>>(dx, dout, n);
+        test_logistic_kernel<<<(n + 255) / 256, 256>>>(dx, dout, n, variant);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpy(out, dout, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost);

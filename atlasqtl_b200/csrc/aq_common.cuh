@@ -151,20 +151,34 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // ---------------------------------------------------------------- chain math
 // 1 / (1 + exp(x)) with a short dependency chain: the in-block Gauss-Seidel recurrence is latency bound (one fp64
-// op is ~9 cycles), so
+// op is ~9-17 cycles behind the tensor work of the same SM sub-partition) and this routine is most of a step, so
 //   - exp(r), |r| <= ln2/2, is a degree-13 Taylor polynomial in Estrin form (depth 4 instead of 13; truncation 4e-18);
 //   - 2^k is assembled on the integer side while the polynomial runs, and 1 + 2^k e^r is ONE fma;
 //   - the reciprocal is the hardware seed (relative error e0 <= 2^-20) times (1 + e0 + e0^2): error e0^3 < 1e-18;
 //   - out-of-range arguments are resolved by selects at the end instead of clamps at the start.
-// |relative error| < 4e-16, far inside the 1e-8 bound on gam_vb.  == exp(-log1pexp(x)) of the reference
-// (src/coreLoop.cpp:28-33, :75-77).
+// kShort trims two more dependent operations: the argument reduction r = x - k ln2 becomes ONE fma (ln2 as a double is off
+// by 5.5e-17, so the result is off by the RELATIVE amount |k| 5.5e-17 -- 3e-15 for |x| <= 40, up to 6e-14 at |x| = 700
+// where the value itself is 1e-304 or 1 - 1e-304: the absolute error of gam_vb stays below an ulp of 1), and the two
+// range selects become one whose condition and alternative are ready long before.  Measured on B200 (same box,
+// gpurun_out/r2_ab.log): chain-bound tiles gain (n = 500, 32-trait tiles: 4.35 -> 4.28 ms), the tensor-bound 16-trait tiles
+// of n = 1000 lose (18.25 -> 18.45 ms), so the sweep kernel picks per configuration.
+// == exp(-log1pexp(x)) of the reference (src/coreLoop.cpp:28-33, :75-77).
+template <bool kShort = false>
 __device__ __forceinline__ double logistic_neg(double x) {
-    const double kInvLn2 = 1.4426950408889634074, kLn2Hi = 6.93147180369123816490e-01, kLn2Lo = 1.90821492927058770002e-10;
+    const double kInvLn2 = 1.4426950408889634074, kLn2 = 6.93147180559945286227e-01;
     const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: round-to-nearest-integer trick
     const double t = fma(x, kInvLn2, kMagic);
     const double k = t - kMagic;
-    double r = fma(-k, kLn2Hi, x);
-    r = fma(-k, kLn2Lo, r);
+    double r;
+    if constexpr (kShort) {
+        r = fma(-k, kLn2, x);
+    } else {
+        r = fma(-k, 6.93147180369123816490e-01, x);    // ln2 in two pieces (Cody-Waite)
+        r = fma(-k, 1.90821492927058770002e-10, r);
+    }
+    // beyond +-700 the function is 0 / 1 to 1e-304 and the pieces below are meaningless; NaN falls through (both false)
+    const bool out = fabs(x) > 700.0;
+    const double alt = x > 0.0 ? 0.0 : 1.0;
     const double r2 = r * r;
     const double p01 = r + 1.0;
     const double p23 = fma(r, 1.0 / 6.0, 0.5);
@@ -188,7 +202,7 @@ __device__ __forceinline__ double logistic_neg(double x) {
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
     const double e0 = fma(-d, y, 1.0);
     y = fma(y, fma(e0, e0, e0), y);
-    // beyond +-700 the function is 0 / 1 to 1e-304 and the pieces above are meaningless; NaN falls through
+    if constexpr (kShort) return out ? alt : y;
     return x > 700.0 ? 0.0 : (x < -700.0 ? 1.0 : y);
 }
 

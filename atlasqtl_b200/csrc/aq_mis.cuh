@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(128, (M <= 16) ? 4 : 2) mis_sweep_kernel(const
                 const double ap_t = __shfl_sync(0xffffffffu, ap, t);
                 const double s = fma(bo_t, xn_t, dot);                 // :120, :125
                 const double m = a_t * s;                              // :125
-                const double gm = logistic_neg(fma(s * s, -bq_t, ap_t));   // :127-129
+                const double gm = logistic_neg<>(fma(s * s, -bq_t, ap_t));   // :127-129
                 dlt = fma(gm, m, -bo_t);                               // :131-132
                 if (lane == t) { gnew = gm; mnew = m; }
             } else {

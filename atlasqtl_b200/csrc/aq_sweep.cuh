@@ -117,6 +117,9 @@ struct SweepCfg {
     static constexpr int kXS = kNPad + ((kNPad % 16 == 0) ? 8 : 0);  // tile row stride == 8 (mod 16) doubles
     static constexpr int kThreads = 16 * 32;  // warps 3 (chain) and 7 (helper) + 14 MMA warps (two of them on SMSP 3)
     static constexpr int kStages = 3;
+    // the chain's logistic with two dependent operations less (aq_common.cuh): wins where the serial chain bounds a block
+    // (clusters, missing responses, 24- / 32-trait tiles of small n), loses on the tensor-bound 16-trait tiles
+    static constexpr bool kShortLogistic = CL_ || MIS_ || MT_ != 2;
     // where the pending S phase is finished inside the rank-8 update (see AQ_S_FINISH_AT); with 3 or 4 M tiles per warp the
     // S accumulators kept alive across the phase boundary would cost register spills in the MMA loops: never pipelined there
     static constexpr int kSFin = (MT_ <= 2) ? AQ_S_FINISH_AT : -1;
@@ -130,8 +133,21 @@ struct SweepCfg {
     static constexpr size_t kSpartDoubles = (size_t)WS * kT * kSps;      // [WS][kT][kSps], single-buffered (sfree barrier)
     // who sums the split-K partials of S: the chain warp itself (single CTA: one hop less between the tensor work and the
     // recurrence), or the helper warp (clusters: the wait for the other CTAs' slices stays off the serial path)
-    static constexpr bool kChainSums = !kCl && MT > 1;
-    static constexpr size_t kSsumDoubles = kChainSums ? 0 : (size_t)2 * kT * kSps;  // [2][kT][kSps] summed S tile for the chain
+    static constexpr bool kChainSums = MT > 1;
+    // cluster leader: the helper warp sums the other CTAs' S tiles while the chain warp sums this CTA's own partials
+    // (n = 5000, 8 CTAs: chain does both 24.99 ms, in parallel 23.74 ms; helper does both, as in round 1: 28.4 ms)
+    static constexpr bool kHelperSumsFollowers = kCl && kChainSums;
+    // who forwards -Delta to the other CTAs of a cluster in sweep mode: the leader's MMA warps when they start the update
+    // (448 threads, ~2 stores each) -- or the chain warp itself, straight from its registers, before it publishes locally
+    // (28 stores per lane, but the followers' copy leaves a barrier wake-up and a shared-memory round trip earlier).  The
+    // helper warp doing it after the publish was far slower (n = 5000: 23.7 -> 34.8 ms, gpurun_out/r2_ab4.log).
+#ifdef AQ_AB_CHAIN_FWD
+    static constexpr bool kChainForwards = kCl && kChainSums;
+#else
+    static constexpr bool kChainForwards = false;
+#endif
+    // [2][kT][kSps] S tile handed from the helper to the chain: the whole sum (8-trait tiles) or the followers' part of it
+    static constexpr size_t kSsumDoubles = (kChainSums && !kHelperSumsFollowers) ? 0 : (size_t)2 * kT * kSps;
     static constexpr size_t kDbufDoubles = (size_t)2 * kT * kBlk;
     static constexpr size_t kRsqDoubles = (size_t)WS * kT;
     // [2][kBlk][kIoPer][kT]: in beta_old, c (D + cst) (+ a, bq per pair with missing responses); out gam, mu
@@ -223,6 +239,34 @@ __device__ __forceinline__ void sum_own_partials(double (&s)[kBlk], const double
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&sfree[0]);  // the MMA warps may overwrite the partials
+}
+
+// Cluster leader: the S tiles the other CTAs reduced and shipped here (st.async, accounted on sred).  Lane = trait; with
+// <= 16 traits per tile the two half-warps split the CTAs and the halves are added at the end.
+template <class Cfg>
+__device__ __forceinline__ void sum_follower_tiles(double (&s)[kBlk], const double* red, uint64_t* sred, long gb, int ncta,
+                                                   int lane, int tsum) {
+    constexpr int kT = Cfg::kT;
+    constexpr int kH = (kT <= 16) ? 2 : 1;
+    const int half = (kH == 2) ? (lane >> 4) : 0;
+#pragma unroll
+    for (int t = 0; t < kBlk; ++t) s[t] = 0.0;
+    if (lane == 0) mbar_arrive_expect_tx(&sred[gb & 1], (uint32_t)(ncta - 1) * Cfg::kDeltaBytes);
+    mbar_wait(&sred[gb & 1], (uint32_t)((gb >> 1) & 1));
+    const int mid = (kH == 2) ? (ncta + 1) / 2 : ncta;
+    for (int r2 = (half == 0 ? 1 : mid); r2 < (half == 0 ? mid : ncta); ++r2) {
+        const double* rp = red + (size_t)((gb & 1) * (kMaxCluster - 1) + (r2 - 1)) * kT * Cfg::kSps;
+#pragma unroll
+        for (int t = 0; t < kBlk; t += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(rp + sp_off(tsum, t));
+            s[t] += v.x;
+            s[t + 1] += v.y;
+        }
+    }
+    if (kH == 2) {
+#pragma unroll
+        for (int t = 0; t < kBlk; ++t) s[t] += __shfl_xor_sync(0xffffffffu, s[t], 16);
+    }
 }
 
 // S = X_b' R of one block: this CTA's partials and, on a cluster leader, the tiles the other CTAs shipped.
@@ -498,7 +542,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                 AQ_T(14);
                 const double* xt = tiles + stage * Cfg::kTileDoubles;
                 const double* db = dbuf + (size_t)(gb & 1) * kT * kBlk;
-                if (kCl && rank == 0) {
+                if (kCl && rank == 0 && !(Cfg::kChainForwards && P.mode == 0)) {
                     // leader: forward the kT x 8 block of -Delta to every follower, one 16-byte asynchronous DSMEM store per
                     // lane, accounted on the follower's barrier (armed by its reducer warp)
                     constexpr int kV2 = kT * kBlk / 2;
@@ -751,6 +795,22 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                         }
                     }
                     if (blk + 1 < un.b1) stage_rows(blk + 1);
+                    if constexpr (Cfg::kHelperSumsFollowers) {
+                        // the other CTAs' S tiles, summed here while the chain warp sums this CTA's own partials
+                        if (ncta > 1) {
+                            double s[kBlk];
+                            sum_follower_tiles<Cfg>(s, red, sred, g, ncta, lane, tls);
+                            if (half == 0 && active) {
+#pragma unroll
+                                for (int t = 0; t < kBlk; t += 2) {
+                                    double2 v;
+                                    v.x = s[t];
+                                    v.y = s[t + 1];
+                                    *reinterpret_cast<double2*>(ssum + (size_t)(g & 1) * kT * Cfg::kSps + sp_off(tl, t)) = v;
+                                }
+                            }
+                        }
+                    }
                     if (!Cfg::kChainSums) {
                         AQ_T(4);
                         double s[kBlk];
@@ -896,6 +956,16 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
         // a remote operation, they would sit in its load/store queue on the serial path
         auto publish = [&](long gb, const double (&nd)[kBlk]) {
             double* dblk = dbuf + (size_t)(gb & 1) * kT * kBlk;
+            if constexpr (Cfg::kChainForwards) {
+                if (P.mode == 0 && active) {
+                    for (int r2 = 1; r2 < ncta; ++r2) {
+                        const uint32_t rbar = mapa_u32(&dready[gb & 1], r2);
+#pragma unroll
+                        for (int t = 0; t < kBlk; t += 2)
+                            st_async_v2(mapa_u32(dblk + d_off<kT>(tl, t), r2), nd[t], nd[t + 1], rbar);
+                    }
+                }
+            }
             if (active) {
 #pragma unroll
                 for (int t = 0; t < kBlk; t += 2) {
@@ -933,9 +1003,19 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                     const double* gband = kMis ? gkbuf + (size_t)(gb & 1) * 128 * kT + tsum
                                                : tiles + stage * Cfg::kTileDoubles + kBlk * XS;
                     constexpr int gstride = kMis ? kT : 1;
-                    mbar_wait(&inready[gb & 1], (uint32_t)((gb >> 1) & 1));   // beta_old, c (D + cst): staged a block ahead
                     double* io = iobuf + (size_t)(gb & 1) * kBlk * kIoPer * kT;
                     double s[kBlk], bo[kBlk], ap[kBlk], nd[kBlk], av[kMis ? kBlk : 1], bv[kMis ? kBlk : 1];
+                    if constexpr (Cfg::kHelperSumsFollowers) {
+                        // clusters: this CTA's partials first (they only need the MMA warps), then the inputs and the other
+                        // CTAs' part of S, both prepared by the helper warp meanwhile
+                        AQ_T(0);
+                        sum_own_partials<Cfg>(s, spart, sdone, sfree, gb, lane, tsum);
+                        if (kT <= 16) {
+#pragma unroll
+                            for (int t = 0; t < kBlk; ++t) s[t] += __shfl_xor_sync(0xffffffffu, s[t], 16);
+                        }
+                    }
+                    mbar_wait(&inready[gb & 1], (uint32_t)((gb >> 1) & 1));   // beta_old, c (D + cst): staged a block ahead
 #pragma unroll
                     for (int t = 0; t < kBlk; ++t) {
                         bo[t] = io[(t * kIoPer + 0) * kT + tsum];
@@ -945,7 +1025,17 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                             bv[t] = io[(t * kIoPer + 3) * kT + tsum];
                         }
                     }
-                    if (Cfg::kChainSums) {
+                    if constexpr (Cfg::kHelperSumsFollowers) {
+                        if (ncta > 1) {
+                            const double* sp0 = ssum + (size_t)(gb & 1) * kT * Cfg::kSps;
+#pragma unroll
+                            for (int t = 0; t < kBlk; t += 2) {
+                                const double2 v = *reinterpret_cast<const double2*>(sp0 + sp_off(tsum, t));
+                                s[t] += v.x;
+                                s[t + 1] += v.y;
+                            }
+                        }
+                    } else if (Cfg::kChainSums) {
                         // S = X_b' R: this warp sums the split-K partials itself the moment the MMA warps have delivered
                         // them; no other warp sits between the tensor work and the recurrence
                         AQ_T(0);
@@ -972,7 +1062,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) sweep_kernel(const SweepPara
                         const double st = s[t];
                         const double m = (kMis ? av[kMis ? t : 0] : a) * st;                        // :73  (:125)
                         const double x = fma(st * st, -(kMis ? bv[kMis ? t : 0] : bq), ap[t]);      // :75-77  (:127-129)
-                        const double gm = logistic_neg(x);                   // 1/(1+e^x) == exp(-log1pexp(x))
+                        const double gm = logistic_neg<Cfg::kShortLogistic>(x);   // 1/(1+e^x) == exp(-log1pexp(x))
                         const double dlt = fma(gm, m, -bo[t]);               // :79 beta_new - beta_old (0 for padding slots)
                         const double* grow = gband + t * 16 * gstride;       // row t: [next block | this block]
 #pragma unroll

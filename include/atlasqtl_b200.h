@@ -272,9 +272,10 @@ int aq_sweep_plan(const aq_ctx* ctx, int* traits_per_tile, int* ntiles, int* gro
 /*
  * Test hook: out[i] = the sweep's annealed logistic 1 / (1 + exp(x[i])) evaluated ON THE DEVICE with the very routine
  * the chain warp uses (== exp(-logOnePlusExp(x)), src/coreLoop.cpp:28-33, :75-77), so that its range handling
- * (|x| > 700, NaN) can be checked directly.  x, out: host arrays of length n.
+ * (|x| > 700, NaN) can be checked directly.  variant: 0 = two-constant argument reduction (tensor-bound 16-trait tiles),
+ * 1 = the shorter dependency chain the chain-bound configurations use.  x, out: host arrays of length n.
  */
-int aq_test_logistic(int device, const double* x, double* out, int n);
+int aq_test_logistic(int device, int variant, const double* x, double* out, int n);
 
 #ifdef __cplusplus
 }
