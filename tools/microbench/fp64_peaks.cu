@@ -126,10 +126,13 @@ __global__ void k_lat(double* out, long long* cyc, int iters, double x0) {
     out[threadIdx.x] = x + y + z + w + s + d0 + d1 + r + sh;
 }
 
+// best-of-`reps` CUDA-event time of one launch; < 0 if the launch itself fails (e.g. too many registers for the block size)
 template <typename F>
 float timeit(F f, int reps = 5) {
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    f(); CK(cudaDeviceSynchronize());
+    f();
+    if (cudaGetLastError() != cudaSuccess) return -1.f;
+    CK(cudaDeviceSynchronize());
     float best = 1e30f;
     for (int r = 0; r < reps; r++) {
         CK(cudaEventRecord(e0)); f(); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
@@ -149,25 +152,30 @@ int main() {
         int threads = warps * 32; int blocks = sms * (warps <= 16 ? 2 : 1);
         float ms = timeit([&] { k_dfma<<<blocks, threads>>>(out, iters, 0.999, 1e-3); });
         double flops = 2.0 * 16 * iters * (double)threads * blocks;
-        printf("DFMA   blocks %d x %d thr: %.2f TFLOP/s\n", blocks, threads, flops / ms / 1e9);
+        if (ms > 0) printf("DFMA   blocks %d x %d thr: %.2f TFLOP/s\n", blocks, threads, flops / ms / 1e9);
     }
     for (int warps : {4, 8, 16, 32}) {
         int threads = warps * 32; int blocks = sms * (warps <= 16 ? 2 : 1);
         float ms = timeit([&] { k_mma884<8><<<blocks, threads>>>(out, iters, 0.999, 1e-3); });
         double flops = 2.0 * 256 * 8 * iters * (double)warps * blocks;
-        printf("DMMA m8n8k4   x8acc blocks %d x %d thr: %.2f TFLOP/s\n", blocks, threads, flops / ms / 1e9);
+        if (ms > 0) printf("DMMA m8n8k4   x8acc blocks %d x %d thr: %.2f TFLOP/s\n", blocks, threads, flops / ms / 1e9);
+        else printf("DMMA m8n8k4   x8acc blocks %d x %d thr: not launchable (registers)\n", blocks, threads);
         ms = timeit([&] { k_mma884<2><<<blocks, threads>>>(out, iters, 0.999, 1e-3); });
         flops = 2.0 * 256 * 2 * iters * (double)warps * blocks;
-        printf("DMMA m8n8k4   x2acc blocks %d x %d thr: %.2f TFLOP/s\n", blocks, threads, flops / ms / 1e9);
+        if (ms > 0) printf("DMMA m8n8k4   x2acc blocks %d x %d thr: %.2f TFLOP/s\n", blocks, threads, flops / ms / 1e9);
+        else printf("DMMA m8n8k4   x2acc blocks %d x %d thr: not launchable (registers)\n", blocks, threads);
         ms = timeit([&] { k_mma16<8, 4><<<blocks, threads>>>(out, iters, 0.999, 1e-3); });
         flops = 2.0 * 512 * 8 * iters * (double)warps * blocks;
-        printf("DMMA m16n8k4  x8acc blocks %d x %d thr: %.2f TFLOP/s\n", blocks, threads, flops / ms / 1e9);
+        if (ms > 0) printf("DMMA m16n8k4  x8acc blocks %d x %d thr: %.2f TFLOP/s\n", blocks, threads, flops / ms / 1e9);
+        else printf("DMMA m16n8k4  x8acc blocks %d x %d thr: not launchable (registers)\n", blocks, threads);
         ms = timeit([&] { k_mma16<8, 8><<<blocks, threads>>>(out, iters, 0.999, 1e-3); });
         flops = 2.0 * 1024 * 8 * iters * (double)warps * blocks;
-        printf("DMMA m16n8k8  x8acc blocks %d x %d thr: %.2f TFLOP/s\n", blocks, threads, flops / ms / 1e9);
+        if (ms > 0) printf("DMMA m16n8k8  x8acc blocks %d x %d thr: %.2f TFLOP/s\n", blocks, threads, flops / ms / 1e9);
+        else printf("DMMA m16n8k8  x8acc blocks %d x %d thr: not launchable (registers)\n", blocks, threads);
         ms = timeit([&] { k_mma16<8, 16><<<blocks, threads>>>(out, iters, 0.999, 1e-3); });
         flops = 2.0 * 2048 * 8 * iters * (double)warps * blocks;
-        printf("DMMA m16n8k16 x8acc blocks %d x %d thr: %.2f TFLOP/s\n", blocks, threads, flops / ms / 1e9);
+        if (ms > 0) printf("DMMA m16n8k16 x8acc blocks %d x %d thr: %.2f TFLOP/s\n", blocks, threads, flops / ms / 1e9);
+        else printf("DMMA m16n8k16 x8acc blocks %d x %d thr: not launchable (registers)\n", blocks, threads);
     }
     int lit = 2000;
     k_lat<<<1, 32>>>(out, cyc, lit, 0.5); CK(cudaDeviceSynchronize());
