@@ -90,37 +90,54 @@ bool pick_nt_mis(int nt, bool cl, int ncta, CfgInfo* out) {
     if constexpr (NT < kMaxNTMis) return pick_nt_mis<NT + 1>(nt, cl, ncta, out);
     return false;
 }
-bool pick_cfg_mis(int n, CfgInfo* out) {
+// Which cluster size?  A cluster of c CTAs holds ceil(n / (112 c)) sample tiles per warp; smaller slices mean wider trait
+// tiles (more traits per serial chain step) but more CTAs to synchronise per block and fewer clusters per GPU.  Model,
+// fitted to sweeps timed on B200 (gpurun_out/r2_*.log: n = 1500 / 3000 / 5000, 2..8 CTAs):
+//   cycles per 8-SNP block  =  256 MT NT (tensor pipe: 4 warps per sub-partition x 4 MT NT DMMAs x 16 cycles)
+//                              + 1500 (S reduction -> chain -> -Delta hand-off across the cluster; + 500 for 8 CTAs)
+//   clusters resident at once on 148 SMs:  74 / 49 / 33 / 22 / 15  for  2 / 3 / 4 / 6 / 8 CTAs  (5 and 7 place badly)
+//   cost  =  rounds of the persistent grid x cycles per block  =  ceil(tiles / clusters) x ...
+// and the cheapest candidate wins: the choice depends on q_local through the number of rounds (C3 on one GPU, n = 3000,
+// q = 1500: 4 CTAs, 3 rounds of 16-trait tiles; C5 on 8 GPUs, n = 5000, q_local = 2500: 6 CTAs).
+int clusters_resident(int ncta, int sm_count) {
+    const int on148 = ncta == 1 ? 148 : ncta == 2 ? 74 : ncta == 3 ? 49 : ncta == 4 ? 33 : ncta == 6 ? 22 : 15;
+    return std::max(1, (int)((long)on148 * sm_count / 148));
+}
+template <class Pick>
+bool pick_by_cost(int n, int q, int sm_count, int max_nt_single, int max_nt_cl, int (*mt_of)(int, bool), Pick pick, CfgInfo* out) {
     const char* fc = std::getenv("AQ_FORCE_CLUSTER");
-    int ncta = fc ? std::atoi(fc) : 0;
-    if (!(ncta >= 2 && ncta <= kMaxCluster)) {
-        ncta = 0;
-        for (int cand : {1, 2, 4, 6, 8})
-            if (n <= cand * 112 * (cand > 1 ? kMaxNTMisCl : kMaxNTMis)) { ncta = cand; break; }
-        if (!ncta) return false;
-    } else if (n > ncta * 112 * kMaxNTMisCl) return false;
-    const int nt = (n + 112 * ncta - 1) / (112 * ncta);
-    return pick_nt_mis<1>(nt, ncta > 1, ncta, out);
+    const int forced = fc ? std::atoi(fc) : 0;
+    double best = 0.0;
+    int best_c = 0;
+    for (int c : {1, 2, 3, 4, 6, 8}) {
+        if (forced >= 1 && forced <= kMaxCluster && c != forced) continue;
+        const int nt = (n + 112 * c - 1) / (112 * c);
+        if (nt > (c == 1 ? max_nt_single : max_nt_cl)) continue;
+        const int mt = mt_of(nt, c > 1);
+        const long tiles = (q + 8 * mt - 1) / (8 * mt);
+        const long rounds = (tiles + clusters_resident(c, sm_count) - 1) / clusters_resident(c, sm_count);
+        const double cost = (double)rounds * (256.0 * mt * nt + (c == 1 ? 600.0 : 1500.0) + (c == 8 ? 500.0 : 0.0));
+        if (c == 1) { best_c = 1; break; }   // one CTA whenever the samples fit: no cluster traffic at all
+        if (!best_c || cost < best) { best = cost; best_c = c; }
+    }
+    if (forced >= 2 && forced <= kMaxCluster && !best_c) {   // a forced size outside the candidate list (5, 7)
+        const int nt = (n + 112 * forced - 1) / (112 * forced);
+        if (nt <= max_nt_cl) best_c = forced;
+    }
+    if (!best_c) return false;
+    const int nt = (n + 112 * best_c - 1) / (112 * best_c);
+    return pick(nt, best_c > 1, best_c, out);
+}
+int mt_dense(int nt, bool cl) { return mt_of_nt(nt, cl); }
+int mt_mis(int, bool) { return 2; }
+
+bool pick_cfg_mis(int n, int q, int sm_count, CfgInfo* out) {
+    return pick_by_cost(n, q, sm_count, kMaxNTMis, kMaxNTMisCl, mt_mis, pick_nt_mis<1>, out);
 }
 
-bool pick_cfg(int n, CfgInfo* out) {
-    // development knob: AQ_FORCE_CLUSTER=2..8 selects the sample-split cluster kernel with that many CTAs per cluster
-    // (even where one CTA suffices); by default the smallest power of two that holds the samples
-    const char* fc = std::getenv("AQ_FORCE_CLUSTER");
-    int ncta = fc ? std::atoi(fc) : 0;
-    const bool forced = ncta >= 2 && ncta <= kMaxCluster;
-    if (!forced) ncta = 1;
-    // 2688 < n <= 3360 (C3: n = 3000): six CTAs of <= 560 samples hold 32-trait tiles (4 M tiles per warp) where four CTAs
-    // hold 16-trait ones, and 24 such clusters cover 144 SMs where 33 clusters of four cover 132.  Measured at n = 3000,
-    // p = 8000, q = 1500 (gpurun_out/r2d.log): 4 CTAs 11.24 ms, 5: 10.85, 6: 10.35, 7: 13.03, 8: 13.41.
-    if (!forced && n > 2688 && n <= 3360) ncta = 6;
-    while (n > ncta * 112 * (ncta > 1 ? kMaxNTCl : kMaxNT)) {
-        if (forced) return false;
-        ncta *= 2;
-        if (ncta > kMaxCluster) return false;
-    }
-    const int nt = (n + 112 * ncta - 1) / (112 * ncta);
-    return pick_nt<1>(nt, ncta > 1, ncta, out);
+// development knob for both: AQ_FORCE_CLUSTER=1..8 fixes the number of CTAs per cluster
+bool pick_cfg(int n, int q, int sm_count, CfgInfo* out) {
+    return pick_by_cost(n, q, sm_count, kMaxNT, kMaxNTCl, mt_dense, pick_nt<1>, out);
 }
 
 }  // namespace
@@ -626,12 +643,12 @@ namespace {
 int create_impl(aq_ctx** out, int device, int n, int p, int q_local, const double* X, const aq_prep* prep, const double* Y,
                 double* n_obs) {
     if (n < 2 || p < 1 || q_local < 1) return fail(AQ_EINVAL, "aq_create: need n >= 2, p >= 1, q >= 1");
-    CfgInfo cfg;
-    if (!pick_cfg(n, &cfg))
-        return fail(AQ_EUNSUPPORTED, "aq_create: n > 7168 is beyond the 8-CTA sample-split cluster kernel");
     int sm = 0;
     int rc = aq_device_info(device, &sm, nullptr, nullptr);
     if (rc != AQ_OK) return rc;
+    CfgInfo cfg;
+    if (!pick_cfg(n, q_local, sm, &cfg))
+        return fail(AQ_EUNSUPPORTED, "aq_create: n > 7168 is beyond the 8-CTA sample-split cluster kernel");
     aq_ctx* c = new aq_ctx();
     c->device = device;
     c->n = n;
@@ -1352,7 +1369,7 @@ int aq_set_missing(aq_ctx* c, const double* mis_pat, double* n_obs) {
     const char* force = std::getenv("AQ_MIS_KERNEL");
     const bool want_warp = force && std::strcmp(force, "warp") == 0, want_tile = force && std::strcmp(force, "tile") == 0;
     CfgInfo cfgm;
-    bool tile_ok = !want_warp && pick_cfg_mis(c->n, &cfgm);
+    bool tile_ok = !want_warp && pick_cfg_mis(c->n, c->q, c->sm_count, &cfgm);
     if (tile_ok) {
         size_t fr = 0, tot = 0;
         AQ_CUDA(cudaMemGetInfo(&fr, &tot));
