@@ -60,7 +60,7 @@ def _host_threads():
     return max(1, min(32, ncpu // share))
 
 
-def _pmap(fn, x, min_chunk=4096):
+def _pmap(fn, x, min_chunk=1024):
     """Apply an element-wise SciPy special function over a long p-vector on all host threads (the ufunc inner loops
     release the GIL).  These are the only non-trivial host costs per iteration: exp1 / gammaincc at p = 50k take
     tens of milliseconds single-threaded, comparable to the GPU sweep once the traits are spread over 8 GPUs."""

@@ -261,20 +261,21 @@ int launch_sweep_t(aq_ctx* c, int slot, SweepParams P, int ntiles, int k_base) {
     lc.blockDim = dim3(C::kThreads);
     lc.dynamicSmemBytes = C::kSmemBytes;
     lc.stream = c->stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     lc.attrs = attr;
     lc.numAttrs = 0;
     if (C::kCl) {
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = ncta;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        lc.numAttrs = 1;
-    } else if (P.nseg > 1) {
+        attr[lc.numAttrs].id = cudaLaunchAttributeClusterDimension;
+        attr[lc.numAttrs].val.clusterDim.x = ncta;
+        attr[lc.numAttrs].val.clusterDim.y = 1;
+        attr[lc.numAttrs].val.clusterDim.z = 1;
+        lc.numAttrs++;
+    }
+    if (P.nseg > 1) {
         // CTAs hand trait tiles over to one another inside the launch: all of them must be resident at the same time
-        attr[0].id = cudaLaunchAttributeCooperative;
-        attr[0].val.cooperative = 1;
-        lc.numAttrs = 1;
+        attr[lc.numAttrs].id = cudaLaunchAttributeCooperative;
+        attr[lc.numAttrs].val.cooperative = 1;
+        lc.numAttrs++;
     }
     P.ntiles = ntiles;
     P.k_base = k_base;
@@ -288,7 +289,7 @@ int launch_sweep_t(aq_ctx* c, int slot, SweepParams P, int ntiles, int k_base) {
 
 // How the trait tiles are spread over the persistent grid.  A grid of G CTAs (clusters) processes G tiles per round and
 // a partly filled last round costs as much as a full one.  Two remedies, whichever the block-count model below prefers:
-//  (a) segmented sweep (single-CTA configurations): the SNP blocks of every tile are cut into S segments and the
+//  (a) segmented sweep: the SNP blocks of every tile are cut into S segments and the
 //      (segment, tile) units dealt round-robin, so the last round costs 1 / S of a round; a unit costs its blocks plus
 //      ~kSegOverheadBlocks (pipeline fill / drain, residual reload);
 //  (b) leftover traits that fit into one round of 8-trait tiles are swept by the MT = 1 variant of the configuration
@@ -319,7 +320,7 @@ SweepPlan plan_sweep(const aq_ctx* c, int G, int kT, bool clustered, bool has_ta
             }
         }
     }
-    if (!clustered && ntiles > G && !std::getenv("AQ_NO_SEG")) {
+    if (ntiles > G && !std::getenv("AQ_NO_SEG") && !(clustered && std::getenv("AQ_NO_SEG_CLUSTER"))) {
         const char* force = std::getenv("AQ_NSEG");
         for (int S = 2; S <= 64 && nb / S >= 16; ++S) {
             if (force && S != std::atoi(force)) continue;

@@ -325,13 +325,17 @@ __device__ __forceinline__ void unit_acquire(const SweepParams& P, const Unit& w
         __syncwarp();
     }
 }
-// end of a unit (segmented launches only): every warp of the CTA has finished its global writes of the unit -> publish
+// end of a unit (segmented launches only): every warp of the CTA (of every CTA of the cluster) has finished its global
+// writes of the unit -> publish.  Executed by ALL warps of all CTAs, whatever their role.
 template <class Cfg>
 __device__ __forceinline__ void unit_release(const SweepParams& P, const Unit& w) {
     if (P.nseg > 1) {
         __syncwarp();
-        asm volatile("bar.sync 2, %0;" ::"n"(Cfg::kThreads) : "memory");
-        if (threadIdx.x == 0) {
+        if constexpr (Cfg::kCl) cluster_sync_all();
+        else asm volatile("bar.sync 2, %0;" ::"n"(Cfg::kThreads) : "memory");
+        bool leader = threadIdx.x == 0;
+        if constexpr (Cfg::kCl) leader = leader && cluster_ctarank() == 0;
+        if (leader) {
             __threadfence();
             st_release_gpu(P.seg_done + w.tile, w.seg + 1);
         }

@@ -31,12 +31,16 @@ def _sweep(monkeypatch, X, Y, si, order, env):
     return dict(st0=st0, out=out, out2=out2, st=st, R=R, rows=rows, plan=plan)
 
 
-@pytest.mark.parametrize("n,p,q,nseg", [
-    (100, 400, 4800 + 5, 3),    # 32-trait tiles (151 of them on 148 SMs), 50 blocks in 3 segments
-    (1000, 256, 2400 + 16, 2),  # the C2 configuration (16-trait tiles, 9 sample tiles per warp): 151 tiles, 2 segments
-    (600, 520, 3600, 4),        # 24-trait tiles: 150 tiles, 65 blocks in 4 segments (last one shorter)
+@pytest.mark.parametrize("n,p,q,nseg,cluster", [
+    (100, 400, 4800 + 5, 3, None),    # 32-trait tiles (151 of them on 148 SMs), 50 blocks in 3 segments
+    (1000, 256, 2400 + 16, 2, None),  # the C2 configuration (16-trait tiles, 9 sample tiles per warp): 151 tiles, 2 segments
+    (600, 520, 3600, 4, None),        # 24-trait tiles: 150 tiles, 65 blocks in 4 segments (last one shorter)
+    (1500, 256, 1620, 2, None),       # 3-CTA clusters of 32-trait tiles: 51 tiles on 49 resident clusters
+    (3000, 256, 560, 2, 4),           # 4-CTA clusters of 16-trait tiles (forced): 35 tiles on 33 resident clusters
 ])
-def test_segmented_sweep_matches_oracle_and_unsegmented(oracle_built, monkeypatch, n, p, q, nseg):
+def test_segmented_sweep_matches_oracle_and_unsegmented(oracle_built, monkeypatch, n, p, q, nseg, cluster):
+    if cluster:
+        monkeypatch.setenv("AQ_FORCE_CLUSTER", str(cluster))
     X, Y, hyper, init = make_problem(n, p, q)
     p = X.shape[1]
     si = sweep_inputs(X, Y, init, c=0.8)
