@@ -317,9 +317,11 @@ __device__ __forceinline__ void unit_acquire(const SweepParams& P, const Unit& w
     if (w.seg > 0) {
         if (lane == 0) {
             uint32_t spins = 0;
+            // (a hand-off normally takes microseconds; 2^23 polls are ~1 s.  If the CTAs of the launch are NOT all resident
+            // -- seen under `ncu --set full` with segmented cluster launches -- this traps instead of spinning for minutes)
             while (ld_acquire_gpu(P.seg_done + w.tile) < w.seg) {
                 __nanosleep(64);
-                if (++spins == kSpinLimit) __trap();
+                if (++spins == (1u << 23)) __trap();
             }
         }
         __syncwarp();
