@@ -28,11 +28,64 @@ def get_mu(E_p_t, s2, p):
     return np.sqrt(1 + s2) * stats.norm.ppf(E_p_t / p)  # R/utils.R:236-240
 
 
-def _solve_t02(p, p0):
-    """uniroot on [1e-6, 1e5] (R/set_hyper_init.R:163-175); brentq here."""
+def _zeroin(f, a, b, tol, maxit=1000):
+    """Brent's zeroin as stats::uniroot runs it (R_zeroin2: linear / inverse quadratic interpolation with bisection
+    safeguards, stop when the bracket is shorter than 4 eps |b| + tol), so that root = "uniroot" lands on the very
+    iterate R returns."""
+    eps = np.finfo(np.float64).eps
+    fa, fb = f(a), f(b)
+    if not (np.isfinite(fa) and np.isfinite(fb)) or fa * fb > 0:
+        raise ValueError("f() values at end points not of opposite sign")
+    if fa == 0.0:
+        return a
+    if fb == 0.0:
+        return b
+    c, fc = a, fa
+    for _ in range(maxit + 1):
+        prev_step = b - a
+        if abs(fc) < abs(fb):
+            a, b, c = b, c, b
+            fa, fb, fc = fb, fc, fb
+        tol_act = 2 * eps * abs(b) + tol / 2
+        new_step = (c - b) / 2
+        if abs(new_step) <= tol_act or fb == 0.0:
+            return b
+        if abs(prev_step) >= tol_act and abs(fa) > abs(fb):
+            cb = c - b
+            if a == c:
+                t1 = fb / fa
+                pp, qq = cb * t1, 1.0 - t1
+            else:
+                qq, t1, t2 = fa / fc, fb / fc, fb / fa
+                pp = t2 * (cb * qq * (qq - t1) - (b - a) * (t1 - 1.0))
+                qq = (qq - 1.0) * (t1 - 1.0) * (t2 - 1.0)
+            if pp > 0:
+                qq = -qq
+            else:
+                pp = -pp
+            if pp < (0.75 * cb * qq - abs(tol_act * qq) / 2) and pp < abs(prev_step * qq / 2):
+                new_step = pp / qq
+        if abs(new_step) < tol_act:
+            new_step = tol_act if new_step > 0 else -tol_act
+        a, fa = b, fb
+        b += new_step
+        fb = f(b)
+        if (fb > 0 and fc > 0) or (fb < 0 and fc < 0):
+            c, fc = a, fa
+    return b
+
+
+def _solve_t02(p, p0, root="brentq"):
+    """uniroot on [1e-6, 1e5] (R/set_hyper_init.R:163-175).  root = "brentq" (default) solves the equation to 1e-12;
+    root = "uniroot" stops where R does (default tol = .Machine$double.eps^0.25 = 1.2e-4 on t02) and so reproduces
+    the reference's t02 / n0 to rounding (tests/test_rlite.py) -- the two differ by up to that tolerance."""
     E_p_t, V_p_t = float(p0[0]), float(p0[1])
-    f = lambda x: get_V_p_t(get_mu(E_p_t, x, p), x, p) - V_p_t
+    f = lambda x: float(get_V_p_t(get_mu(E_p_t, x, p), x, p) - V_p_t)
     try:
+        if root == "uniroot":
+            return _zeroin(f, 1e-6, 1e5, np.finfo(np.float64).eps ** 0.25)
+        if root != "brentq":
+            raise TypeError(f"root must be 'brentq' or 'uniroot', not {root!r}")
         return optimize.brentq(f, 1e-6, 1e5, xtol=1e-12, rtol=1e-10)
     except ValueError:
         raise ValueError("No hyperparameter values matching the expectation and variance of the "
@@ -59,13 +112,13 @@ def set_hyper(q, p, eta, kappa, n0, nu, rho, t02):
                 rho=float(rho), t02=float(t02), _class="hyper")
 
 
-def auto_set_hyper_(Y, p, p0):
-    """R/set_hyper_init.R:146-197."""
+def auto_set_hyper_(Y, p, p0, root="brentq"):
+    """R/set_hyper_init.R:146-197.  root: see `_solve_t02`."""
     q = Y.shape[1]
     eta = 1 / np.median(np.nanvar(Y, axis=0, ddof=1))  # apply(Y, 2, var, na.rm = TRUE)
     if not np.isfinite(eta):
         eta = 1e3
-    t02 = _solve_t02(p, p0)
+    t02 = _solve_t02(p, p0, root)
     n0 = get_mu(p0[0], t02, p)
     h = set_hyper(q, p, eta, 1.0, n0, 1e-2, 1.0, t02)
     h["_class"] = "out_hyper"
@@ -94,11 +147,11 @@ def set_init(q, p, gam_vb, mu_beta_vb, sig02_inv_vb, sig2_beta_vb, sig2_theta_vb
                 zeta_vb=np.asarray(zeta_vb, float), _class="init")
 
 
-def auto_set_init_(Y, p, p0, shr_fac_inv, user_seed=None):
+def auto_set_init_(Y, p, p0, shr_fac_inv, user_seed=None, root="brentq"):
     """R/set_hyper_init.R:356-418 (same distributions, NumPy generator)."""
     q = Y.shape[1]
     rng = np.random.default_rng(user_seed)
-    t02 = _solve_t02(p, p0)
+    t02 = _solve_t02(p, p0, root)
     n0 = get_mu(p0[0], t02, p)
     s02 = 1e-4
     gam_vb = stats.norm.cdf(rng.normal(n0, s02 + t02, size=(p, q)))
