@@ -8,12 +8,15 @@ Follows, statement by statement, the global-local (horseshoe, df = 1) core of th
     R/elbo.R                               e_*_ ELBO terms
     R/utils.R:108-146, 172-191, 380-423    annealing ladder, inverse Mills ratio, Q_approx_vec
 
-PARITY STATUS: "parity unpinned" for this file.  R, Rcpp, gsl and nmath are absent from the
-image, so the outer loop cannot be run against the real package; it is a restatement checked
-only by (i) the reference's own runtime invariant (ELBO non-decreasing after annealing,
-R/atlasqtl_global_local_core.R:359-360), (ii) the reference's single test (the tests/testthat/main.R
-recipe converges) and (iii) dual == primal == blocked agreement.  The sweep it calls IS pinned:
-`sweep="reference"` runs the reference's own src/coreLoop.cpp (oracle/_ref).
+PARITY STATUS: pinned against the reference's own R sources as far as this image allows.  R itself (and Rcpp, gsl,
+nmath) is absent, so the reference's unmodified R files are executed by the R evaluator of oracle/rlite (`.Call` bound
+to the reference's own compiled src/coreLoop.cpp) and the outputs are committed as tests/golden/rlite_*.npz
+(tests/golden/make_rlite_golden.py).  This restatement must reproduce them -- ELBO at every evaluation to 1e-12
+relative, identical iteration counts, parameters to 1e-10, with and without annealing / thinning / missing responses,
+and BASELINE config C1 -- in tests/test_rlite.py, which also re-derives the fixtures live where /root/reference exists.
+What remains a stand-in: the evaluator (its R semantics are unit-tested) and SciPy for nmath / gsl (pinned against
+mpmath in tests/test_special_functions.py).  The sweep it calls IS the reference's: `sweep="reference"` runs the
+reference's own src/coreLoop.cpp (oracle/_ref).
 
 Function mapping (SURVEY.md section 8c): pnorm(log.p=TRUE) -> scipy.special.log_ndtr;
 digamma/lgamma -> scipy.special.digamma/gammaln; gsl::expint_E1 -> scipy.special.exp1;

@@ -11,7 +11,6 @@ Here:
     pre-processing mirror, `atlasqtl()`, the hyper-parameter defaults and assign_bFDR are compared with them too;
   * where /root/reference exists (this container, not the GPU box) the fixtures are re-derived live.
 """
-import glob
 import os
 import sys
 
@@ -22,18 +21,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = os.path.join(HERE, "golden")
 sys.path.insert(0, GOLD)
 
-CORE_FILES = sorted(glob.glob(os.path.join(GOLD, "rlite_core_*.npz")))
-HYPER_KEYS = ("q_hyper", "p_hyper", "A2_inv", "eta", "kappa", "m0", "n0", "nu", "rho", "t02")
-INIT_KEYS = ("q_init", "p_init", "gam_vb", "mu_beta_vb", "sig02_inv_vb", "sig2_beta_vb", "sig2_theta_vb", "tau_vb",
-             "theta_vb", "zeta_vb")
-
-
-def load_case(path):
-    g = np.load(path)
-    hyper = {k: (g["hyper_" + k] if g["hyper_" + k].ndim else g["hyper_" + k].item()) for k in HYPER_KEYS}
-    init = {k: (g["init_" + k] if g["init_" + k].ndim else g["init_" + k].item()) for k in INIT_KEYS}
-    anneal = None if np.isnan(g["anneal"][0]) else tuple(float(a) for a in g["anneal"])
-    return g, hyper, init, anneal
+from rlite_cases import CORE_FILES, CORE_IDS, hyper_init_of, load_case  # noqa: E402
 
 
 # --------------------------------------------------------------------------------------------- the evaluator itself
@@ -140,7 +128,7 @@ def test_r_semantics_names_lists_and_match_call():
 
 
 # --------------------------------------------------------------------------------------------- golden vs restatement
-@pytest.mark.parametrize("path", CORE_FILES, ids=[os.path.basename(f)[11:-4] for f in CORE_FILES])
+@pytest.mark.parametrize("path", CORE_FILES, ids=CORE_IDS)
 def test_restated_loop_reproduces_the_reference_r_code(oracle_built, path):
     from oracle import vb_oracle
     g, hyper, init, anneal = load_case(path)
@@ -165,7 +153,7 @@ def test_restated_loop_reproduces_the_reference_r_code(oracle_built, path):
     assert np.array_equal(out["gam_vb"] > 0.5, g["gam_vb"] > 0.5)
 
 
-@pytest.mark.parametrize("path", CORE_FILES, ids=[os.path.basename(f)[11:-4] for f in CORE_FILES])
+@pytest.mark.parametrize("path", CORE_FILES, ids=CORE_IDS)
 def test_product_host_loop_reproduces_the_reference_r_code(oracle_built, path):
     """atlasqtl_b200.core (the loop the CUDA path runs under) with the oracle-backed test double for the device."""
     from atlasqtl_b200 import core
@@ -261,8 +249,7 @@ def test_preprocessing_and_top_level_call_reproduce_the_reference_r_code(oracle_
     pairs = sorted((k, r) for k, rs in dat["rmvd_coll_x"].items() for r in rs)
     assert pairs == sorted(zip(g["prep_rmvd_coll_kept"].tolist(), g["prep_rmvd_coll_x"].tolist()))
     assert dat["names_x"] == list(g["names_x"]) and dat["names_y"] == list(g["names_y"])
-    hyper = {k: (g["hyper_" + k] if g["hyper_" + k].ndim else g["hyper_" + k].item()) for k in HYPER_KEYS}
-    init = {k: (g["init_" + k] if g["init_" + k].ndim else g["init_" + k].item()) for k in INIT_KEYS}
+    hyper, init = hyper_init_of(g)
     trace = []
     out = api.atlasqtl(Y, X, None, anneal=tuple(g["anneal"]), tol=float(g["tol"]), maxit=1000, verbose=0,
                        list_hyper=hyper, list_init=init, trace=trace,
