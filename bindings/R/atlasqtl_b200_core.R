@@ -1,47 +1,327 @@
-# Call-site patch for atlasqtl_global_local_core_ (reference R/atlasqtl_global_local_core.R).
-# Only the lines that touch p x q / n x q objects change; every p-, q- and scalar-sized update_*_vb_
-# helper of R/update_vb.R and every e_*_ term of R/elbo.R is called exactly as before.
-# (atlasqtl_b200/core.py is the same patch written in Python, and is what the tests in this repository run.)
+# atlasqtl_b200: the VB outer loop of the `atlasqtl` R package written against the stateful C ABI
+# (include/atlasqtl_b200.h through the .Call wrappers of bindings/R/atlasqtl_b200_shim.c).
 #
-#   reference lines                         replacement
-#   :40-42   Y_norm_sq, cp_X, cp_Y_X    ->  ctx <- .Call(`_atlasqtl_aq_create`, X, Y, 0L)
-#   :61-63   log_Phi tables             ->  .Call(`_atlasqtl_aq_refresh_tables`, ctx, theta_vb, zeta_vb, c, FALSE)
-#   :112-115 beta_vb, m2_beta, cp_X_Xbeta -> s <- .Call(`_atlasqtl_aq_set_state`, ctx, gam_vb, mu_beta_vb)
-#   :134-135 sum(gam_vb), colSums(m2_beta) -> sum(s$colsum_gam); s$colsum_gam_mu2 + sig2_beta_vb * s$colsum_gam
-#   :141-142 eta_vb, kappa_vb           ->  c * (eta + n/2 + s$colsum_gam/2) - c + 1
-#                                           c * (kappa + (s$resid_sq + (n-1+sig2_inv_vb) * colsum_m2 - (n-1) * s$colsum_beta2)/2)
-#   :162-170 coreDualLoop(...)          ->  s <- .Call(`_atlasqtl_aq_sweep`, ctx, c, log_sig2_inv_vb, tau_vb, log_tau_vb, sig2_beta_vb)
-#   :235-237 m2_beta, Z                 ->  rowsums_Z <- .Call(`_atlasqtl_aq_rowsums_zpart`, ctx, p) / sqrt_c + q * theta_vb + sum(zeta_vb)
-#                                           colsums_Z <- s$colsum_zpart / sqrt_c + sum(theta_vb) + p * zeta_vb
-#   :280,290 rowSums(Z), colSums(Z)     ->  rowsums_Z, colsums_Z in update_theta_vb_ / update_zeta_vb_
-#   :293-295 log_Phi tables             ->  elbo_B_dev <- .Call(`_atlasqtl_aq_refresh_tables`, ctx, theta_vb, zeta_vb, c_next, want_elbo)
-#   :472     e_beta_gamma_(...)         ->  sum(s$colsum_gam * (log_sig2_inv_vb/2 + log_tau_vb/2 + (log(sig2_beta_vb)+1)/2)) -
-#                                           sum(colsum_m2 * tau_vb) * sig2_inv_vb/2 + elbo_B_dev - p*q*sig2_zeta_vb/2 - q*sum(sig2_theta_vb)/2
-#   :418-428 output                     ->  gam_vb <- beta_vb <- matrix(0, p, q); .Call(`_atlasqtl_aq_get_state`, ctx, gam_vb, NULL, beta_vb)
+# A maintainer of the R package replaces the body of `atlasqtl_global_local_core_`
+# (reference R/atlasqtl_global_local_core.R:8-433) by a call to `atlasqtl_b200_core_` below: same arguments, same
+# returned list.  No p x q or n x q object is touched by R inside the loop: the state (gam_vb, mu_beta_vb, the residual,
+# the probit tables) lives on the GPU and every update that the reference writes on matrices is re-expressed through the
+# per-trait / per-SNP sums the sweep returns.  atlasqtl_b200/core.py is the same loop in Python (with trait-slab
+# sharding on top).  The p-, q- and scalar-sized helpers of the package are called unchanged:
+#   get_annealing_ladder_ (R/utils.R:108), update_sig2_c0_vb_, update_nu_vb_, update_log_tau_vb_,
+#   update_log_sig2_inv_vb_, update_annealed_lam2_inv_vb_ (R/update_vb.R), Q_approx_vec (R/utils.R:380),
+#   e_tau_, e_theta_hs_, e_zeta_, e_sig2_inv_, e_sig2_inv_hs_ (R/elbo.R), create_named_list_, checkpoint_,
+#   checkpoint_clean_up_ (R/utils.R).
 #
-# Missing responses (any(is.na(Y)), :19-38 and the mis_pat branches of R/update_vb.R / R/elbo.R):
-#   :21-33   mis_pat, X_norm_sq, cp_X_rm  ->  mis_pat <- ifelse(is.na(Y), 0, 1); Y[is.na(Y)] <- 0
-#                                             n_obs <- .Call(`_atlasqtl_aq_set_missing`, ctx, mis_pat)      # = colSums(mis_pat)
-#   :112-115 (m2_beta with sweep = TRUE)   ->  s <- .Call(`_atlasqtl_aq_set_state_mis`, ctx, gam_vb, mu_beta_vb)
-#                                             colsum_m2 <- s$colsum_gam_mu2 + sig2_beta_vb * s$colsum_gam
-#                                             colsum_xn_m2 <- s$colsum_xn_gam_mu2 + sig2_beta_vb * s$colsum_xn_gam
-#   :141     update_eta_vb_(.., mis_pat)   ->  c * (eta + n_obs/2 + s$colsum_gam/2) - c + 1
-#   :142     update_kappa_vb_(.., X_norm_sq) -> c * (kappa + (s$resid_sq + sig2_inv_vb * colsum_m2 + colsum_xn_m2 - s$colsum_xn_beta2)/2)
-#   :147     update_sig2_beta_vb_(.., X_norm_sq) -> formed on the device inside the sweep (p x q never exists in R)
-#   :172-175 coreDualMisLoop(...)          ->  s <- .Call(`_atlasqtl_aq_sweep_mis`, ctx, c, log_sig2_inv_vb, sig2_inv_vb, tau_vb, log_tau_vb)
-#   :235     m2_beta (p x q sig2_beta_vb)  ->  colsum_m2 <- s$colsum_gam_mu2 + s$colsum_sig2b_gam
-#                                             colsum_xn_m2 <- s$colsum_xn_gam_mu2 + s$colsum_xn_sig2b_gam
-#   :470     e_y_(.., mis_pat)             ->  arg <- n_obs * (log_tau_vb - log(2 * pi)) / 2
-#   :472     e_beta_gamma_ (p x q sig2_beta_vb) -> sum(s$colsum_gam * (log_sig2_inv_vb/2 + log_tau_vb/2 + 1/2) + s$colsum_gam_logsig2b/2) - ...
+# What replaces what (reference line numbers):
+#   :40-42    Y_norm_sq, cp_X, cp_Y_X             aq_create (X tiles + Gram band + Y on the device)
+#   :19-33    mis_pat, X_norm_sq, cp_X_rm         aq_set_missing (returns colSums(mis_pat))
+#   :61-63, :293-295  pnorm(.., log.p = TRUE) x 2  aq_refresh_tables (also returns the p x q part of e_beta_gamma_)
+#   :112-115  beta_vb, m2_beta, cp_X_Xbeta        aq_set_state / aq_set_state_mis (residual + first sums)
+#   :134-150  update_*_vb_ on matrices            the same formulas on s$colsum_* / s$resid_sq
+#   :162-176  coreDualLoop / coreDualMisLoop      aq_sweep / aq_sweep_mis
+#   :235-237  m2_beta, Z                          s$colsum_zpart, aq_rowsums_zpart
+#   :346-354  elbo_global_local_                  terms A, B, E from the sums; C, D, F, G, H unchanged
+#   :414-428  output                              aq_get_state
+#
+# This file is executed in the test-suite by the R evaluator of oracle/rlite (there is no R in the build image) with
+# `.Call` bound to the library (tests/test_r_binding.py, tests/test_gpu_r_binding.py).
 
-coreDualLoop <- function(cp_X, cp_Y_X, gam_vb, log_Phi_theta_plus_zeta, log_1_min_Phi_theta_plus_zeta,
-                         log_sig2_inv_vb, log_tau_vb, m1_beta, cp_betaX_X, mu_beta_vb, sig2_beta_vb, tau_vb,
-                         shuffled_ind, sample_q, c = 1) {
-  # unchanged closure (R/RcppExports.R:4-6): the symbol now resolves to the CUDA-backed shim
-  invisible(.Call(`_atlasqtl_coreDualLoop`, cp_X, cp_Y_X, gam_vb, log_Phi_theta_plus_zeta,
-                  log_1_min_Phi_theta_plus_zeta, log_sig2_inv_vb, log_tau_vb, m1_beta, cp_betaX_X, mu_beta_vb,
-                  sig2_beta_vb, tau_vb, shuffled_ind, sample_q, c))
+atlasqtl_b200_core_ <- function(Y, X, shr_fac_inv, anneal, df, tol, maxit, verbose, list_hyper, list_init,
+                                checkpoint_path = NULL, trace_path = NULL, full_output = FALSE,
+                                thinned_elbo_eval = TRUE, debug = FALSE, batch = "y", device = 0L,
+                                lb_hook = NULL) {   # lb_hook(it, lb_new): called after every ELBO evaluation
+
+  if (batch != "y") stop("Batch scheme not defined. Exit.")
+  if (df != 1) stop("atlasqtl_b200 implements the df = 1 horseshoe (the only value atlasqtl() passes).")
+  if (!is.null(trace_path)) stop("trace_path (plots of the hotspot variances) is not part of this path.")
+
+  n <- nrow(Y)
+  p <- ncol(X)
+  q <- ncol(Y)
+
+  has_na <- any(is.na(Y))
+  if (has_na) {
+    mis_pat <- ifelse(is.na(Y), 0, 1)
+    Y[is.na(Y)] <- 0
+  }
+
+  ctx <- .Call(`_atlasqtl_aq_create`, X, Y, as.integer(device))
+  n_eff <- n
+  if (has_na) n_eff <- .Call(`_atlasqtl_aq_set_missing`, ctx, mis_pat)   # colSums(mis_pat)
+
+  sig02_inv_vb <- list_init$sig02_inv_vb
+  sig2_beta_vb <- list_init$sig2_beta_vb
+  sig2_theta_vb <- list_init$sig2_theta_vb
+  tau_vb <- list_init$tau_vb
+  theta_vb <- list_init$theta_vb
+  zeta_vb <- list_init$zeta_vb
+
+  if (is.null(anneal)) {
+    annealing <- FALSE
+    c <- c_s <- 1
+    it_init <- 1
+  } else {
+    annealing <- TRUE
+    ladder <- get_annealing_ladder_(anneal, verbose)
+    c <- c_s <- ladder[1]
+    it_init <- anneal[3]
+  }
+
+  eps <- .Machine$double.eps^0.5
+
+  if (thinned_elbo_eval) {
+    times_conv_sched <- c(1, 5, 10, 50)
+    batch_conv_sched <- c(1, 10, 25, 50)
+  } else {
+    times_conv_sched <- 1
+    batch_conv_sched <- 1
+  }
+  ind_batch_conv <- length(batch_conv_sched) + 1
+  batch_conv <- 1
+
+  eta <- list_hyper$eta
+  kappa <- list_hyper$kappa
+  n0 <- list_hyper$n0
+  nu <- list_hyper$nu
+  rho <- list_hyper$rho
+  t02 <- list_hyper$t02
+  m0 <- list_hyper$m0
+  A2_inv <- list_hyper$A2_inv
+
+  t02_inv <- 1 / t02
+  sig2_zeta_vb <- update_sig2_c0_vb_(p, t02, c = c)
+  vec_sum_log_det_zeta <- - q * (log(t02) + log(p + t02_inv))
+  nu_xi_inv_vb <- 1
+
+  # first sums: colSums of gam, gam * mu^2, beta^2 and |y_k - X beta_k|^2 (with NAs also their X_norm_sq-weighted twins)
+  colsum_xn_m2 <- NULL
+  if (has_na) {
+    s <- .Call(`_atlasqtl_aq_set_state_mis`, ctx, list_init$gam_vb, list_init$mu_beta_vb)
+    colsum_xn_m2 <- s$colsum_xn_gam_mu2 + sig2_beta_vb * s$colsum_xn_gam
+  } else {
+    s <- .Call(`_atlasqtl_aq_set_state`, ctx, list_init$gam_vb, list_init$mu_beta_vb)
+  }
+  colsum_m2 <- s$colsum_gam_mu2 + sig2_beta_vb * s$colsum_gam        # colSums(m2_beta), q-vector sig2_beta_vb of the init
+  rm(list_init)
+
+  .Call(`_atlasqtl_aq_refresh_tables`, ctx, theta_vb, zeta_vb, c, FALSE)
+
+  kappa_bracket <- function(s, colsum_m2, colsum_xn_m2, sig2_inv_vb) {  # the bracket of update_kappa_vb_
+    if (has_na)
+      s$resid_sq + sig2_inv_vb * colsum_m2 + colsum_xn_m2 - s$colsum_xn_beta2
+    else
+      s$resid_sq + (n - 1 + sig2_inv_vb) * colsum_m2 - (n - 1) * s$colsum_beta2
+  }
+
+  converged <- FALSE
+  lb_new <- -Inf
+  it <- 0
+
+  while ((!converged) & (it < maxit)) {
+
+    lb_old <- lb_new
+    it <- it + 1
+    annealed_iteration <- annealing
+
+    if (verbose != 0 & (it == 1 | it %% max(5, batch_conv) == 0))
+      cat(paste0("Iteration ", format(it), "... \n"))
+
+    nu_vb <- update_nu_vb_(nu, sum(s$colsum_gam), c = c)
+    rho_vb <- c * (rho + sum(tau_vb * colsum_m2) / 2)
+    sig2_inv_vb <- nu_vb / rho_vb
+
+    eta_vb <- c * (eta + n_eff / 2 + s$colsum_gam / 2) - c + 1
+    kappa_vb <- c * (kappa + kappa_bracket(s, colsum_m2, colsum_xn_m2, sig2_inv_vb) / 2)
+    tau_vb <- eta_vb / kappa_vb
+
+    log_tau_vb <- update_log_tau_vb_(eta_vb, kappa_vb)
+    log_sig2_inv_vb <- update_log_sig2_inv_vb_(nu_vb, rho_vb)
+
+    # the horseshoe scale update reads the theta_vb / sig2_theta_vb / sig02_inv_vb of the previous iteration
+    L_vb <- c_s * sig02_inv_vb * shr_fac_inv * (theta_vb^2 + sig2_theta_vb - 2 * theta_vb * m0 + m0^2) / 2 / df
+    rho_xi_inv_vb <- c_s * (A2_inv + sig02_inv_vb)
+
+    if (has_na) {
+      # sig2_beta_vb(j, k) = 1 / (c (X_norm_sq(j, k) + sig2_inv_vb) tau_k) is formed on the device
+      s <- .Call(`_atlasqtl_aq_sweep_mis`, ctx, c, log_sig2_inv_vb, sig2_inv_vb, tau_vb, log_tau_vb)
+      colsum_m2 <- s$colsum_gam_mu2 + s$colsum_sig2b_gam
+      colsum_xn_m2 <- s$colsum_xn_gam_mu2 + s$colsum_xn_sig2b_gam
+    } else {
+      sig2_beta_vb <- 1 / (c * (n - 1 + sig2_inv_vb) * tau_vb)
+      s <- .Call(`_atlasqtl_aq_sweep`, ctx, c, log_sig2_inv_vb, tau_vb, log_tau_vb, sig2_beta_vb)
+      colsum_m2 <- s$colsum_gam_mu2 + sig2_beta_vb * s$colsum_gam
+    }
+
+    # rowSums(Z), colSums(Z) with Z = (gam (imr1 - imr0) + imr0) / sqrt_c + theta_j + zeta_k
+    sqrt_c <- 1
+    if (!isTRUE(all.equal(c, 1))) sqrt_c <- sqrt(c)
+    rowsums_Z <- .Call(`_atlasqtl_aq_rowsums_zpart`, ctx, p) / sqrt_c + q * theta_vb + sum(zeta_vb)
+    colsums_Z <- s$colsum_zpart / sqrt_c + sum(theta_vb) + p * zeta_vb
+
+    if (annealing) {
+      lam2_inv_vb <- update_annealed_lam2_inv_vb_(L_vb, c_s, df)
+    } else {
+      Q_app <- Q_approx_vec(L_vb)
+      lam2_inv_vb <- 1 / (Q_app * L_vb) - 1
+    }
+
+    xi_inv_vb <- nu_xi_inv_vb / rho_xi_inv_vb
+
+    prior_prec <- sig02_inv_vb * lam2_inv_vb * shr_fac_inv
+    sig2_theta_vb <- update_sig2_c0_vb_(q, 1 / prior_prec, c = c)
+    theta_vb <- c * sig2_theta_vb * (rowsums_Z + prior_prec * m0 - sum(zeta_vb))
+
+    nu_s0_vb <- update_nu_vb_(1 / 2, p, c = c_s)
+    rho_s0_vb <- c_s * (xi_inv_vb +
+                          sum(lam2_inv_vb * shr_fac_inv * (theta_vb^2 + sig2_theta_vb - 2 * theta_vb * m0 + m0^2)) / 2)
+    sig02_inv_vb <- as.numeric(nu_s0_vb / rho_s0_vb)
+
+    zeta_vb <- c * sig2_zeta_vb * (colsums_Z + t02_inv * n0 - sum(theta_vb))
+
+    want_elbo <- FALSE
+    c_next <- c
+
+    if (annealing) {
+
+      if (verbose != 0 & (it == 1 | it %% 5 == 0))
+        cat(paste0("Temperature = ", format(1 / c, digits = 4), "\n\n"))
+
+      sig2_zeta_vb <- c * sig2_zeta_vb
+      c_next <- ifelse(it < length(ladder), ladder[it + 1], 1)
+      sig2_zeta_vb <- sig2_zeta_vb / c_next
+
+      if (isTRUE(all.equal(c_next, 1))) {
+        annealing <- FALSE
+        if (verbose != 0) cat("** Exiting annealing mode. **\n\n")
+      }
+
+    } else {
+
+      want_elbo <- it <= it_init + 1 | it %% batch_conv == 0 | it %% batch_conv == 1
+
+    }
+
+    # tables of theta_j + zeta_k for the next sweep; on demand the p x q part of e_beta_gamma_:
+    # sum(gam log Phi + (1 - gam) log(1 - Phi) - gam log(gam + eps) - (1 - gam) log(1 - gam + eps))
+    elbo_B_dev <- .Call(`_atlasqtl_aq_refresh_tables`, ctx, theta_vb, zeta_vb, c_next, want_elbo)
+
+    if (want_elbo) {
+
+      # c = 1 re-derivations of elbo_global_local_ from the post-sweep sums
+      eta_e <- eta + n_eff / 2 + s$colsum_gam / 2
+      kappa_e <- kappa + kappa_bracket(s, colsum_m2, colsum_xn_m2, sig2_inv_vb) / 2
+      nu_e <- update_nu_vb_(nu, sum(s$colsum_gam))
+      rho_e <- rho + sum(tau_vb * colsum_m2) / 2
+
+      log_tau_e <- update_log_tau_vb_(eta_e, kappa_e)
+      log_sig2_inv_e <- update_log_sig2_inv_vb_(nu_e, rho_e)
+      log_sig02_inv_vb <- update_log_sig2_inv_vb_(nu_s0_vb, rho_s0_vb)
+      log_xi_inv_vb <- update_log_sig2_inv_vb_(nu_xi_inv_vb, rho_xi_inv_vb)
+
+      elbo_A <- sum(n_eff * (log_tau_e - log(2 * pi)) / 2 -
+                      tau_vb * (kappa_e - colsum_m2 * sig2_inv_vb / 2 - kappa))
+
+      if (has_na)
+        gam_log_sig2_beta <- s$colsum_gam_logsig2b
+      else
+        gam_log_sig2_beta <- s$colsum_gam * log(sig2_beta_vb)
+
+      elbo_B <- sum(s$colsum_gam * (log_sig2_inv_e / 2 + log_tau_e / 2 + 1 / 2) + gam_log_sig2_beta / 2) -
+        sum(colsum_m2 * tau_vb) * sig2_inv_vb / 2 + elbo_B_dev -
+        p * q * sig2_zeta_vb / 2 - q * sum(sig2_theta_vb) / 2
+
+      elbo_C <- e_theta_hs_(lam2_inv_vb, L_vb, log_sig02_inv_vb + log(shr_fac_inv), m0, theta_vb, Q_app,
+                            sig02_inv_vb * shr_fac_inv, sig2_theta_vb, df)
+      elbo_D <- e_zeta_(zeta_vb, n0, sig2_zeta_vb, t02_inv, vec_sum_log_det_zeta)
+      elbo_E <- e_tau_(eta, eta_e, kappa, kappa_e, log_tau_e, tau_vb)
+      elbo_F <- e_sig2_inv_hs_(xi_inv_vb, nu_s0_vb, log_xi_inv_vb, log_sig02_inv_vb, rho_s0_vb, sig02_inv_vb)
+      elbo_G <- e_sig2_inv_(1 / 2, nu_xi_inv_vb, log_xi_inv_vb, A2_inv, rho_xi_inv_vb, xi_inv_vb)
+      elbo_H <- e_sig2_inv_(nu, nu_e, log_sig2_inv_e, rho, rho_e, sig2_inv_vb)
+
+      lb_new <- as.numeric(elbo_A + elbo_B + elbo_C + elbo_D + elbo_E + elbo_F + elbo_G + elbo_H)
+      if (!is.null(lb_hook)) lb_hook(it, lb_new)
+
+      if (verbose != 0 & (it == it_init | it %% max(5, batch_conv) == 0))
+        cat(paste0("ELBO = ", format(lb_new), "\n\n"))
+
+      if (debug && lb_new + eps < lb_old)
+        stop("ELBO not increasing monotonically. Exit. ")
+
+      diff_lb <- abs(lb_new - lb_old)
+      sum_exceed <- sum(diff_lb > (times_conv_sched * tol))
+
+      if (sum_exceed == 0) {
+        converged <- TRUE
+      } else if (ind_batch_conv > sum_exceed) {
+        ind_batch_conv <- sum_exceed
+        batch_conv <- batch_conv_sched[ind_batch_conv]
+      }
+
+    }
+
+    if (!is.null(checkpoint_path) && !annealed_iteration && it %% 100 == 0) {   # non-annealed branch only, as the reference
+      gam_vb <- matrix(0, p, q)
+      beta_vb <- matrix(0, p, q)          # two allocations: the library fills them in place
+      .Call(`_atlasqtl_aq_get_state`, ctx, gam_vb, NULL, beta_vb)
+      checkpoint_(it, checkpoint_path, beta_vb, gam_vb, theta_vb, zeta_vb, converged, lb_new, lb_old,
+                  lam2_inv_vb = lam2_inv_vb, sig02_inv_vb = sig02_inv_vb,
+                  names_x = colnames(X), names_y = colnames(Y))
+      rm(gam_vb, beta_vb)
+    }
+
+    c <- c_s <- c_next
+
+  }
+
+  checkpoint_clean_up_(checkpoint_path)
+
+  if (verbose != 0) {
+    if (converged) {
+      cat(paste0("Convergence obtained after ", format(it), " iterations. \n",
+                 "Optimal marginal log-likelihood variational lower bound ",
+                 "(ELBO) = ", format(lb_new), ". \n\n"))
+    } else {
+      warning("Maximal number of iterations reached before convergence. Exit.")
+    }
+  }
+
+  lb_opt <- lb_new
+
+  gam_vb <- matrix(0, p, q)
+  beta_vb <- matrix(0, p, q)              # NOT gam_vb <- beta_vb <- matrix(..): the two names would share one buffer
+  .Call(`_atlasqtl_aq_get_state`, ctx, gam_vb, NULL, beta_vb)
+  .Call(`_atlasqtl_aq_destroy`, ctx)
+
+  if (full_output) {
+
+    create_named_list_(beta_vb, eta_vb, gam_vb, kappa_vb, lam2_inv_vb, nu_s0_vb, nu_vb, nu_xi_inv_vb, rho_s0_vb,
+                       rho_vb, rho_xi_inv_vb, shr_fac_inv, sig02_inv_vb, sig2_inv_vb, sig2_theta_vb, sig2_zeta_vb,
+                       tau_vb, theta_vb, xi_inv_vb, zeta_vb)
+
+  } else {
+
+    names_x <- colnames(X)
+    names_y <- colnames(Y)
+
+    rownames(gam_vb) <- rownames(beta_vb) <- names_x
+    colnames(gam_vb) <- colnames(beta_vb) <- names_y
+    names(theta_vb) <- names_x
+    names(zeta_vb) <- names_y
+
+    diff_lb <- abs(lb_opt - lb_old)
+
+    create_named_list_(beta_vb, gam_vb, theta_vb, zeta_vb, n, p, q, anneal, converged, it, maxit, tol, lb_opt,
+                       diff_lb)
+
+  }
+
 }
+
+
+# The stateless entries keep the generated closures of the reference (R/RcppExports.R:4-10) as they are; only the
+# symbols they name now resolve to the CUDA-backed shim (bindings/R/atlasqtl_b200_shim.c, zero R changes):
+#   coreDualLoop(...)     -> .Call(`_atlasqtl_coreDualLoop`, ... 15 arguments ...)
+#   coreDualMisLoop(...)  -> .Call(`_atlasqtl_coreDualMisLoop`, ... 16 arguments ...)
 #
 # Pre-processing on the device (prepare_data_, R/prepare_atlasqtl.R:57-83; optional, see INTEGRATION.md section 2e):
 #   :57-72   scale(X), rm_constant_, rm_collinear_  ->  pr <- .Call(`_atlasqtl_aq_prep_x`, X, 0L)   # or _atlasqtl_aq_prep_geno
