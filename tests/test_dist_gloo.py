@@ -20,7 +20,7 @@ def _with_nans(Y, frac):
     return Ym
 
 
-def _worker(rank, world, port, tmpdir, anneal, nan_frac=0.0):
+def _worker(rank, world, port, tmpdir, anneal, nan_frac=0.0, golden=None):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     import torch.distributed as dist
@@ -28,8 +28,13 @@ def _worker(rank, world, port, tmpdir, anneal, nan_frac=0.0):
     from atlasqtl_b200.dist import TorchComm, slab_bounds
     from fake_context import OracleSweepContext
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
-    X, Y, hyper, init = make_problem(100, 75, 21, p_act=10, q_act=20, maf=0.2, p0=(5, 25))
-    Y = _with_nans(Y, nan_frac)
+    if golden is not None:   # inputs of a fixture made by the reference's own R code (tests/golden/rlite_core_*.npz)
+        from rlite_cases import load_case
+        g, hyper, init, anneal = load_case(golden)
+        X, Y = g["X"], g["Y"]
+    else:
+        X, Y, hyper, init = make_problem(100, 75, 21, p_act=10, q_act=20, maf=0.2, p0=(5, 25))
+        Y = _with_nans(Y, nan_frac)
     q = Y.shape[1]
     k0, k1 = slab_bounds(q, rank, world)
     comm = TorchComm()
@@ -72,6 +77,22 @@ def test_two_slabs_reproduce_single_process(oracle_built, tmp_path, anneal, nan_
     assert np.abs(d["gam"] - one["gam_vb"]).max() <= 1e-10
     np.testing.assert_allclose(d["theta"], one["theta_vb"], rtol=1e-9, atol=1e-11)
     np.testing.assert_allclose(d["zeta"], one["zeta_vb"], rtol=1e-9, atol=1e-11)
+
+
+@pytest.mark.parametrize("case", ["b_geometric", "e_missing_anneal"])
+def test_two_slabs_reproduce_the_reference_r_code(oracle_built, tmp_path, case):
+    """The sharded run (2 ranks over gloo, one all-reduce per sweep) against outputs of the reference's own R code."""
+    from rlite_cases import GOLD, load_case
+    path = os.path.join(GOLD, f"rlite_core_{case}.npz")
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), None, 0.0, path), nprocs=2, join=True)
+    d = np.load(tmp_path / "dist.npz")
+    g = load_case(path)[0]
+    assert int(d["it"]) == int(g["it"])
+    np.testing.assert_allclose(d["lbs"], g["lb"], rtol=1e-10)
+    assert np.abs(d["gam"] - g["gam_vb"]).max() <= 1e-9
+    np.testing.assert_allclose(d["theta"], g["theta_vb"], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(d["zeta"], g["zeta_vb"], rtol=1e-8, atol=1e-10)
 
 
 class _PpiContext:
