@@ -15,8 +15,8 @@ import numpy as np
 from scipy import special as sp
 
 from . import parser as P
-from .values import (Builtin, Closure, Env, Lang, Promise, RError, RList, V, as_dbl, as_num, chr_, dbl, intv, lgl,
-                     scalar, truthy)
+from .values import (Builtin, Closure, Env, Lang, RError, RList, V, as_dbl, as_num, chr_, dbl, intv, lgl, scalar,
+                     truthy)
 
 LD = np.longdouble
 
@@ -389,10 +389,6 @@ def _flag(v, default):
 
 def _ldsum(a, axis=None):
     return np.sum(a.astype(LD), axis=axis).astype(np.float64)
-
-
-def _copy_attrs(x, a):
-    return V(a, x.names, x.dimnames)
 
 
 def _strs(v):
@@ -794,10 +790,9 @@ def b_sweep(it, pos, named):
         fun = it.lookup_fn(fun.a[0], it.globalenv)
     s = stats.flat()
     ext = x.a.shape[margin - 1]
-    if s.size != ext and not (s.size == 1 or ext % s.size == 0):
-        it.warn("STATS does not recycle exactly across MARGIN")
     if s.size != ext:
-        it.warn("length(STATS) differs from the extent of MARGIN") if s.size != 1 and ext % s.size else None
+        if s.size == 0 or ext % s.size:
+            it.warn("STATS does not recycle exactly across MARGIN")  # check.margin = TRUE
         s = np.resize(s, ext)
     # aperm(array(STATS, dims[perm]), order(perm)): STATS laid along MARGIN, constant along the other
     full = np.repeat(s.reshape(-1, 1), x.a.shape[1], axis=1) if margin == 1 else np.repeat(s.reshape(1, -1),
@@ -1434,10 +1429,6 @@ def b_uniroot(it, pos, named):
 
 
 # ---------------------------------------------------------------------------------------- special forms
-def s_function_env(fn):
-    return Builtin(fn, fn.__name__, special=True)
-
-
 def sp_with(it, env, args):
     data = it.eval(args[0][1], env)
     wenv = Env(env)
@@ -1576,10 +1567,6 @@ def b_do_call(it, pos, named):
 def b_file_path(it, pos, named):
     parts = [_strs(v) for v in pos]
     return chr_([os.path.join(*[p[0] for p in parts])])
-
-
-def b_floor_like(fn):
-    return math1(fn)
 
 
 def b_nchar(it, pos, named):

@@ -5,8 +5,6 @@ evaluated supplied arguments (their expressions are kept for substitute() / matc
 calls (`f(x) <- v`, `x[i] <- v`, `x$a <- v`, nested), copy-on-assign for replacement (values are never modified in
 place by R-level code), function lookup that skips non-function bindings (so a variable named `c` does not hide c()).
 """
-import numpy as np
-
 from . import parser as P
 from .values import (Builtin, Closure, Env, Lang, Promise, RError, RList, V, chr_, dbl, intv, lgl, truthy)
 

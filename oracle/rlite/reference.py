@@ -15,7 +15,7 @@ import numpy as np
 
 from .. import native
 from .interp import Interp
-from .values import Builtin, RError, RList, V, chr_, from_py, to_py
+from .values import Builtin, RError, RList, chr_, from_py, to_py
 
 REF = os.environ.get("ATLASQTL_REFERENCE", "/root/reference")
 R_FILES = ("utils.R", "update_vb.R", "elbo.R", "RcppExports.R", "atlasqtl_global_local_core.R",
