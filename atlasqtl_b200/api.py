@@ -12,8 +12,10 @@ from . import core, hyper_init, prepare
 def atlasqtl(Y, X, p0, anneal=(1, 2, 10), tol=0.1, maxit=1000, user_seed=None, verbose=1, list_hyper=None,
              list_init=None, save_hyper=False, save_init=False, full_output=False, thinned_elbo_eval=True,
              checkpoint_path=None, trace_path=None, add_collinear_back=False, *, device=0, comm=None, order_fn=None,
-             trace=None, context_factory=None, prepare_on_device=False, packed_n=None):
-    """prepare_on_device=True runs prepare_data_'s X / Y work on the GPU (X standardised there, never materialised on
+             trace=None, context_factory=None, prepare_on_device=False, packed_n=None, hyper_root="uniroot"):
+    """hyper_root: how the default hyper-parameters / starting values solve for t02 -- "uniroot" stops where R's uniroot
+    does (its default tolerance), reproducing the reference's t02 / n0; "brentq" solves the equation to 1e-12.
+    prepare_on_device=True runs prepare_data_'s X / Y work on the GPU (X standardised there, never materialised on
     the host); with packed_n = n, X holds packed 2-bit genotype calls (`device.pack_genotypes`) instead of doubles."""
     if verbose not in (0, 1, 2):
         raise ValueError("The verbose argument must be set to 0, 1 or 2.")
@@ -31,7 +33,7 @@ def atlasqtl(Y, X, p0, anneal=(1, 2, 10), tol=0.1, maxit=1000, user_seed=None, v
         if p0 is None or len(p0) != 2 or min(p0) <= 0:
             raise ValueError("p0 must be a vector of two positive numbers.")
     if list_hyper is None:
-        list_hyper = hyper_init.auto_set_hyper_(Yp, p, p0)
+        list_hyper = hyper_init.auto_set_hyper_(Yp, p, p0, root=hyper_root)
     elif list_hyper["p_hyper"] != p or list_hyper["q_hyper"] != q:
         raise ValueError("The dimensions of list_hyper do not match those of the (pre-processed) data.")
     if list_init is None:
@@ -40,7 +42,7 @@ def atlasqtl(Y, X, p0, anneal=(1, 2, 10), tol=0.1, maxit=1000, user_seed=None, v
             # the seed of an unseeded run is drawn once, on rank 0, and shared (all-reduce of [seed, 0, 0, ...])
             seed0 = float(np.random.SeedSequence().entropy % (1 << 52)) if comm.rank == 0 else 0.0
             user_seed = int(comm.allreduce_sum(np.array([seed0]))[0])
-        list_init = hyper_init.auto_set_init_(Yp, p, p0, shr_fac_inv, user_seed)
+        list_init = hyper_init.auto_set_init_(Yp, p, p0, shr_fac_inv, user_seed, root=hyper_root)
     elif list_init["p_init"] != p or list_init["q_init"] != q:
         raise ValueError("The dimensions of list_init do not match those of the (pre-processed) data.")
     if add_collinear_back:

@@ -306,3 +306,13 @@ def test_reference_test_recipe_converges_through_its_own_r_code(oracle_built):
     vb = to_py(vb)
     assert bool(vb["converged"][0])
     assert vb["gam_vb"].shape == (pp, q) and int(vb["it"][0]) < 1000
+    # the product's atlasqtl() on the same call: default hyper-parameters (uniroot's iterate for t02, as R), default
+    # annealing ladder, pre-processing, the loop -- against the reference's own atlasqtl()
+    from atlasqtl_b200 import api
+    from fake_context import OracleSweepContext
+    out = api.atlasqtl(Y, X, (5.0, 25.0), verbose=0, list_init=init, save_hyper=True,
+                       context_factory=lambda X_, Y_: OracleSweepContext(X_, Y_))
+    assert out["converged"] and out["it"] == int(vb["it"][0])
+    assert abs(out["lb_opt"] - float(vb["lb_opt"][0])) <= 1e-8 * abs(out["lb_opt"])
+    assert np.abs(out["gam_vb"] - vb["gam_vb"]).max() <= 1e-7
+    assert np.abs(out["beta_vb"] - vb["beta_vb"]).max() <= 1e-7
