@@ -18,6 +18,10 @@ from .interp import Interp
 from .values import Builtin, RError, RList, chr_, from_py, to_py
 
 REF = os.environ.get("ATLASQTL_REFERENCE", "/root/reference")
+# > 1: one .Call to coreDualLoop is issued as that many concurrent calls on disjoint ranges of sample_q.  Traits are
+# independent inside the loop (column k of every in-place argument is touched by trait k only, src/coreLoop.cpp:58-85),
+# so the results are those of the single call; used for the BASELINE-size golden runs only.
+THREADS = int(os.environ.get("RLITE_REF_THREADS", "1"))
 R_FILES = ("utils.R", "update_vb.R", "elbo.R", "RcppExports.R", "atlasqtl_global_local_core.R",
            "summarise_output.R", "prepare_atlasqtl.R", "set_hyper_init.R", "atlasqtl.R")
 
@@ -38,11 +42,18 @@ def _dot_call(it, pos, named):
     args = pos[1:]
     if sym == "_atlasqtl_coreDualLoop":
         (cp_X, cp_Y_X, gam, lphi, l1phi, lsig, ltau, m1, cpb, mu, s2b, tau, shuf, sq, c) = args
-        native.core_dual_loop(_f64(cp_X, "cp_X"), _f64(cp_Y_X, "cp_Y_X"), _f64(gam, "gam_vb"), _f64(lphi, "log_Phi"),
-                              _f64(l1phi, "log_1_min_Phi"), float(lsig.a[0]), _f64(ltau, "log_tau_vb"),
-                              _f64(m1, "m1_beta"), _f64(cpb, "cp_betaX_X"), _f64(mu, "mu_beta_vb"),
-                              _f64(s2b, "sig2_beta_vb"), _f64(tau, "tau_vb"), shuf.a.astype(np.int32),
-                              sq.a.astype(np.int32), c=float(c.a[0]), impl="reference")
+        fixed = (_f64(cp_X, "cp_X"), _f64(cp_Y_X, "cp_Y_X"), _f64(gam, "gam_vb"), _f64(lphi, "log_Phi"),
+                 _f64(l1phi, "log_1_min_Phi"), float(lsig.a[0]), _f64(ltau, "log_tau_vb"), _f64(m1, "m1_beta"),
+                 _f64(cpb, "cp_betaX_X"), _f64(mu, "mu_beta_vb"), _f64(s2b, "sig2_beta_vb"), _f64(tau, "tau_vb"),
+                 shuf.a.astype(np.int32))
+        sample_q = sq.a.astype(np.int32)
+        if THREADS > 1 and sample_q.size >= 2 * THREADS:
+            from concurrent.futures import ThreadPoolExecutor
+            parts = [np.ascontiguousarray(a) for a in np.array_split(sample_q, THREADS)]
+            with ThreadPoolExecutor(THREADS) as ex:
+                list(ex.map(lambda part: native.core_dual_loop(*fixed, part, c=float(c.a[0]), impl="reference"), parts))
+        else:
+            native.core_dual_loop(*fixed, sample_q, c=float(c.a[0]), impl="reference")
         return None
     if sym == "_atlasqtl_coreDualMisLoop":
         (cp_X, cp_X_rm, cp_Y_X, gam, lphi, l1phi, lsig, ltau, m1, cpb, mu, s2b, tau, shuf, sq, c) = args

@@ -20,6 +20,9 @@ Files
   rlite_c1.npz            BASELINE config C1 (n=200, p=500, q=1000, no annealing) through the same route: ELBO
                           sequence, it, probes -- the existing c1_trajectory.npz (made by oracle/vb_oracle.py) must
                           agree with it (tests/test_rlite.py)
+  rlite_c4.npz            BASELINE config C4 (n=500, p=10000, q=5000, 20 hotspots, annealing; `c4`, not in the default
+                          list: ~1.5 h with RLITE_REF_THREADS=8) -- same check against c4_trajectory.npz, incl. the
+                          {bFDR < 0.05} set formed by the reference's own assign_bFDR
 """
 import os
 import sys
@@ -228,17 +231,39 @@ def make_c1(it):
     save("rlite_c1.npz", in_check=mt.input_checksums(X, Y, hyper, init), **res)
 
 
-def run_core_light(it, X, Y, hyper, init, anneal, tol):
+def make_c4(it):
+    """BASELINE config C4 (n=500, p=10000, q=5000, 20 hotspots, anneal=c(1,2,10), tol = 30 as c4_trajectory.npz) through
+    the reference's own R code and its own dual-form loop: ~50 M pair updates of p-long axpys per iteration, run with
+    RLITE_REF_THREADS concurrent calls on disjoint sample_q ranges (about 1.5 h on 8 cores)."""
+    import make_trajectory as mt
+    t0 = time.time()
+    X, Y, hyper, init, anneal = mt.problem("C4")
+    print(f"  C4 inputs in {time.time() - t0:.0f} s", flush=True)
+    res = run_core_light(it, X, Y, plain(hyper, HYPER_KEYS), plain(init, INIT_KEYS), anneal, 30.0, t0=t0, with_fdr=it)
+    print(f"  C4: it={res['it']} evaluations={len(res['lb'])} [{time.time() - t0:.0f} s]", flush=True)
+    save("rlite_c4.npz", in_check=mt.input_checksums(X, Y, hyper, init), **res)
+
+
+def run_core_light(it, X, Y, hyper, init, anneal, tol, t0=None, with_fdr=None):
     from oracle.rlite import reference as R
+    from oracle.rlite.values import from_py
     lbs = []
-    out = R.global_local_core(Y, X, Y.shape[1], anneal, 1, tol, 1000, hyper, init, it=it,
-                              hook=lambda n, v: lbs.append(v), debug=True)
+
+    def hook(n, v):
+        lbs.append(v)
+        if t0 is not None:
+            print(f"    ELBO evaluation {len(lbs)}: {v!r} [{time.time() - t0:.0f} s]", flush=True)
+    out = R.global_local_core(Y, X, Y.shape[1], anneal, 1, tol, 1000, hyper, init, it=it, hook=hook, debug=True)
     gam = out["gam_vb"].flatten(order="F")
     probe = np.random.default_rng(5).integers(0, gam.size, size=20000)
-    return dict(lb=np.array(lbs), it=int(out["it"][0]), converged=bool(out["converged"][0]),
-                lb_opt=float(out["lb_opt"][0]), probe_idx=probe, probe_gam=gam[probe],
-                probe_beta=out["beta_vb"].flatten(order="F")[probe], theta_vb=out["theta_vb"], zeta_vb=out["zeta_vb"],
-                sum_gam=float(gam.sum()), sel_ppi=np.flatnonzero(gam > 0.5))
+    res = dict(lb=np.array(lbs), it=int(out["it"][0]), converged=bool(out["converged"][0]),
+               lb_opt=float(out["lb_opt"][0]), probe_idx=probe, probe_gam=gam[probe],
+               probe_beta=out["beta_vb"].flatten(order="F")[probe], theta_vb=out["theta_vb"], zeta_vb=out["zeta_vb"],
+               sum_gam=float(gam.sum()), sel_ppi=np.flatnonzero(gam > 0.5))
+    if with_fdr is not None:   # the reference's own assign_bFDR (R/summarise_output.R:207-223) on the final gam_vb
+        fdr = with_fdr.call("assign_bFDR", from_py(out["gam_vb"])).a
+        res["sel_fdr"] = np.flatnonzero(fdr.flatten(order="F") < 0.05)
+    return res
 
 
 def main():
@@ -251,7 +276,7 @@ def main():
     what = sys.argv[1:] or ["functions", "core", "top", "c1"]
     for w in what:
         print(w, flush=True)
-        {"functions": make_functions, "core": make_core, "top": make_top, "c1": make_c1}[w](it)
+        {"functions": make_functions, "core": make_core, "top": make_top, "c1": make_c1, "c4": make_c4}[w](it)
     if it.warnings:
         print("R warnings raised during the runs:", sorted(set(it.warnings)))
 

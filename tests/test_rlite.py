@@ -192,6 +192,31 @@ def test_c1_golden_trajectory_agrees_with_the_reference_r_code():
     assert abs(float(a["sum_gam"]) - float(b["sum_gam"])) <= 1e-9
 
 
+def test_c4_golden_trajectory_agrees_with_the_reference_r_code():
+    """The same for BASELINE config C4 (n=500, p=10000, q=5000, 20 hotspots, anneal = c(1, 2, 10)) -- the config north_star
+    designates for the ELBO-trajectory and PPI / bFDR selection parity check: c4_trajectory.npz (primal restatement,
+    what the GPU C4 test compares with) against the run of the reference's own R code over its own dual-form loop, the
+    {bFDR < 0.05} set formed by the reference's own assign_bFDR."""
+    path = os.path.join(GOLD, "rlite_c4.npz")
+    if not os.path.exists(path):
+        pytest.skip("rlite_c4.npz has not been generated (make_rlite_golden.py c4, ~1.5 h)")
+    a = np.load(os.path.join(GOLD, "c4_trajectory.npz"))
+    b = np.load(path)
+    np.testing.assert_allclose(a["in_check"], b["in_check"], rtol=1e-12)
+    assert int(a["it"]) == int(b["it"]) and bool(a["converged"]) and bool(b["converged"])
+    assert a["lb"].shape == b["lb"].shape
+    assert np.max(np.abs(a["lb"] - b["lb"]) / np.abs(b["lb"])) <= 1e-11
+    assert np.array_equal(a["sel_ppi"], b["sel_ppi"])
+    assert np.array_equal(a["sel_fdr"], b["sel_fdr"])
+    np.testing.assert_allclose(a["theta_vb"], b["theta_vb"], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(a["zeta_vb"], b["zeta_vb"], rtol=1e-8, atol=1e-10)
+    assert abs(float(a["sum_gam"]) - float(b["sum_gam"])) <= 1e-7
+    common, ia, ib = np.intersect1d(a["probe_idx"], b["probe_idx"], return_indices=True)
+    assert len(common) > 10000
+    assert np.abs(a["probe_gam"][ia] - b["probe_gam"][ib]).max() <= 1e-9
+    assert np.abs(a["probe_beta"][ia] - b["probe_beta"][ib]).max() <= 1e-9
+
+
 # --------------------------------------------------------------------------------------------- functions
 def test_function_level_fixtures(oracle_built):
     from atlasqtl_b200 import hyper_init, summarise
