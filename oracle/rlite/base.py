@@ -931,6 +931,26 @@ def _dimnames_set(k):
     return f
 
 
+def b_dimnames(it, pos, named):
+    x = pos[0]
+    if isinstance(x, V) and x.a.ndim == 2 and x.dimnames is not None:
+        return RList([None if d is None else chr_(d) for d in x.dimnames])
+    return None
+
+
+def b_dimnames_assign(it, pos, named):
+    x, val = pos[0], named["value"]
+    if not isinstance(x, V) or x.a.ndim != 2:
+        raise RError("'dimnames' applied to non-array")
+    if val is None:
+        return V(x.a, None, None, x.attrs)
+    dn = [None if d is None else (list(d.flat()) if d.a.dtype.kind == "O" else _strs(d)) for d in val.items]
+    for k in (0, 1):
+        if dn[k] is not None and len(dn[k]) != x.a.shape[k]:
+            raise RError(f"length of 'dimnames' [{k + 1}] not equal to array extent")
+    return V(x.a, None, dn if any(d is not None for d in dn) else None, x.attrs)
+
+
 def b_setNames(it, pos, named):
     x = _arg(pos, named, 0, "object")
     nm = _arg(pos, named, 1, "nm")
@@ -1629,7 +1649,8 @@ def install(it):
                      ("apply", b_apply), ("lapply", b_lapply), ("sapply", b_sapply), ("unlist", b_unlist),
                      ("names", b_names), ("names<-", b_names_assign), ("rownames", _dimnames_get(0)),
                      ("colnames", _dimnames_get(1)), ("rownames<-", _dimnames_set(0)),
-                     ("colnames<-", _dimnames_set(1)), ("setNames", b_setNames), ("class", b_class),
+                     ("colnames<-", _dimnames_set(1)), ("setNames", b_setNames), ("dimnames", b_dimnames),
+                     ("dimnames<-", b_dimnames_assign), ("class", b_class),
                      ("class<-", b_class_assign), ("inherits", b_inherits), ("attr", b_attr),
                      ("attr<-", b_attr_assign), ("as.vector", b_as_vector), ("as.numeric", b_as_numeric),
                      ("as.double", b_as_numeric), ("as.integer", b_as_integer), ("as.character", b_as_character),
