@@ -341,3 +341,35 @@ def test_reference_test_recipe_converges_through_its_own_r_code(oracle_built):
     assert abs(out["lb_opt"] - float(vb["lb_opt"][0])) <= 1e-8 * abs(out["lb_opt"])
     assert np.abs(out["gam_vb"] - vb["gam_vb"]).max() <= 1e-7
     assert np.abs(out["beta_vb"] - vb["beta_vb"]).max() <= 1e-7
+
+
+def test_reference_r_statement_of_the_sweep_equals_its_compiled_loop(oracle_built):
+    """batch = "0" (R/atlasqtl_global_local_core.R:179-227) states the per-pair update in plain R -- pnorm(log.p),
+    log_one_plus_exp_, the rank-1 correction of cp_X_Xbeta -- where batch = "y" calls the compiled coreDualLoop /
+    coreDualMisLoop.  With `sample()` returning the identity order (the order coreDualLoop is given, :162-163) the two
+    must walk the same trajectory: a check of the reference against itself, of the evaluator's handling of the in-place
+    `.Call`, and of SciPy's log-CDF against the C++ loop's inputs."""
+    R = _live()
+    from oracle.rlite.values import Builtin, intv
+    import make_rlite_golden as mk
+    for name, size in (("b_geometric", (40, 18, 5)), ("e_missing_anneal", (40, 14, 4))):
+        n, p, q = size
+        X, Y, hyper, init, anneal, thinned, tol = mk.core_case(name)
+        X, Y = np.asfortranarray(X[:n, :p]), np.asfortranarray(Y[:n, :q])
+        hyper = dict(hyper, q_hyper=q, p_hyper=p, eta=hyper["eta"][:q], kappa=hyper["kappa"][:q], n0=hyper["n0"][:q])
+        init = dict(init, q_init=q, p_init=p, gam_vb=init["gam_vb"][:p, :q], mu_beta_vb=init["mu_beta_vb"][:p, :q],
+                    sig2_beta_vb=init["sig2_beta_vb"][:q], sig2_theta_vb=init["sig2_theta_vb"][:p],
+                    tau_vb=init["tau_vb"][:q], theta_vb=init["theta_vb"][:p], zeta_vb=init["zeta_vb"][:q])
+        it = R.load()
+        it.globalenv.vars["sample"] = Builtin(lambda it_, pos, named: intv(pos[0].flat()), "sample")   # identity order
+        runs = {}
+        for batch in ("y", "0"):
+            lbs = []
+            out = R.global_local_core(Y, X, q, anneal, 1, tol, 200, hyper, init, it=it, hook=lambda k, v: lbs.append(v),
+                                      batch=batch, debug=True)
+            runs[batch] = (out, np.array(lbs))
+        (a, la), (b, lb) = runs["y"], runs["0"]
+        assert int(a["it"][0]) == int(b["it"][0]) and la.shape == lb.shape
+        np.testing.assert_allclose(la, lb, rtol=1e-12)
+        assert np.abs(a["gam_vb"] - b["gam_vb"]).max() <= 1e-11
+        assert np.abs(a["beta_vb"] - b["beta_vb"]).max() <= 1e-11
