@@ -373,3 +373,95 @@ def test_reference_r_statement_of_the_sweep_equals_its_compiled_loop(oracle_buil
         np.testing.assert_allclose(la, lb, rtol=1e-12)
         assert np.abs(a["gam_vb"] - b["gam_vb"]).max() <= 1e-11
         assert np.abs(a["beta_vb"] - b["beta_vb"]).max() <= 1e-11
+
+
+def test_set_hyper_and_set_init_mirror_the_reference_constructors(oracle_built):
+    """set_hyper / set_init (R/set_hyper_init.R:98-140, :311-351): same fields for valid arguments (scalars recycled
+    to q), and the arguments the reference rejects are rejected."""
+    R = _live()
+    from atlasqtl_b200 import hyper_init
+    from oracle.rlite.values import RError, from_py, to_py
+    it = R.load()
+    q, p = 4, 6
+    rng = np.random.default_rng(2)
+
+    def r_hyper(**kw):
+        a = dict(q=float(q), p=float(p), eta=1.5, kappa=2.0, n0=-2.0, nu=0.01, rho=1.0, t02=0.2)
+        a.update(kw)
+        return it.call("set_hyper", *[from_py(a[k]) for k in ("q", "p", "eta", "kappa", "n0", "nu", "rho", "t02")])
+    h_r = to_py(r_hyper())
+    h_p = hyper_init.set_hyper(q, p, 1.5, 2.0, -2.0, 0.01, 1.0, 0.2)
+    for k in ("A2_inv", "eta", "kappa", "m0", "n0", "nu", "rho", "t02", "q_hyper", "p_hyper"):
+        np.testing.assert_allclose(np.asarray(h_p[k], dtype=float).reshape(-1), np.asarray(h_r[k], dtype=float).reshape(-1))
+    h_r = to_py(r_hyper(eta=np.array([1.0, 2.0, 3.0, 4.0])))
+    np.testing.assert_allclose(hyper_init.set_hyper(q, p, [1.0, 2.0, 3.0, 4.0], 2.0, -2.0, 0.01, 1.0, 0.2)["eta"], h_r["eta"])
+    for bad in (dict(t02=-1.0), dict(nu=0.0), dict(eta=np.array([1.0, -1.0, 1.0, 1.0])), dict(kappa=np.array([1.0, 2.0]))):
+        with pytest.raises(RError):
+            r_hyper(**bad)
+        with pytest.raises(ValueError):
+            a = dict(eta=1.5, kappa=2.0, n0=-2.0, nu=0.01, rho=1.0, t02=0.2)
+            a.update(bad)
+            hyper_init.set_hyper(q, p, a["eta"], a["kappa"], a["n0"], a["nu"], a["rho"], a["t02"])
+
+    good = dict(gam_vb=np.asfortranarray(rng.uniform(size=(p, q))), mu_beta_vb=np.asfortranarray(rng.normal(size=(p, q))),
+                sig02_inv_vb=3.0, sig2_beta_vb=rng.uniform(0.5, 1, q), sig2_theta_vb=rng.uniform(0.5, 1, p),
+                tau_vb=rng.uniform(0.5, 1, q), theta_vb=rng.normal(size=p), zeta_vb=rng.normal(size=q))
+    order = ("gam_vb", "mu_beta_vb", "sig02_inv_vb", "sig2_beta_vb", "sig2_theta_vb", "tau_vb", "theta_vb", "zeta_vb")
+
+    def r_init(**kw):
+        a = dict(good)
+        a.update(kw)
+        return it.call("set_init", from_py(float(q)), from_py(float(p)), *[from_py(a[k]) for k in order])
+    i_r = to_py(r_init())
+    i_p = hyper_init.set_init(q, p, *[good[k] for k in order])
+    for k in order + ("q_init", "p_init"):
+        np.testing.assert_allclose(np.asarray(i_p[k], dtype=float), np.asarray(i_r[k], dtype=float).reshape(np.shape(i_p[k])))
+    bad_gam = good["gam_vb"].copy()
+    bad_gam[0, 0] = 1.5
+    for bad in (dict(gam_vb=bad_gam), dict(tau_vb=-good["tau_vb"]), dict(theta_vb=good["theta_vb"][:-1]),
+                dict(mu_beta_vb=good["mu_beta_vb"][:, :-1]), dict(sig02_inv_vb=-1.0)):
+        with pytest.raises(RError):
+            r_init(**bad)
+        with pytest.raises(ValueError):
+            a = dict(good)
+            a.update(bad)
+            hyper_init.set_init(q, p, *[a[k] for k in order])
+
+
+def test_argument_checks_mirror_the_reference(oracle_built):
+    """check_annealing_ (R/prepare_atlasqtl.R:101-128) and the data checks of prepare_data_ (:11-45): what the reference
+    accepts is accepted, what it refuses is refused."""
+    R = _live()
+    from atlasqtl_b200 import core, prepare
+    from oracle.rlite.values import RError, from_py
+    it = R.load()
+    for anneal, ok in (((1, 2, 10), True), ((2, 3, 7), True), ((3, 1.5, 2), True), (None, True), ((4, 2, 10), False),
+                       ((1, 1.2, 10), False), ((1, 2, 1001), False), ((1, 2), False), ((1, 2, 2.5), False),
+                       ((0, 2, 10), False), ((1, -2, 10), False)):
+        arg = None if anneal is None else from_py(np.array(anneal, dtype=np.float64))
+        if ok:
+            it.call("check_annealing_", arg)
+            core.check_annealing_(anneal)
+        else:
+            with pytest.raises(RError):
+                it.call("check_annealing_", arg)
+            with pytest.raises((ValueError, TypeError)):
+                core.check_annealing_(anneal)
+    rng = np.random.default_rng(4)
+    X = rng.binomial(2, 0.3, size=(40, 12)).astype(np.float64)
+    Y = rng.normal(size=(40, 5))
+    few = np.full_like(Y, np.nan)
+    few[:1, :] = 1.0                       # < 5 % non-NA overall
+    col = Y.copy()
+    col[:, 2] = np.nan                     # one column > 97.5 % NA
+    edge = col.copy()
+    edge[0, 2] = 0.3                       # exactly 2.5 % observed: `< 0.025` does not fire, in either
+    it.call("prepare_data_", from_py(edge), from_py(X), from_py(0.1), from_py(10.0), None, from_py(0.0), None, None)
+    prepare.prepare_data_(edge, X, 0.1, 10)
+    for Yb, Xb, tol, maxit in ((few, X, 0.1, 10), (col[:, :], X, 0.1, 10), (Y[:-1], X, 0.1, 10), (Y, X, -1.0, 10),
+                               (Y, X, 0.1, 2.5), (Y, np.ones_like(X), 0.1, 10)):
+        with pytest.raises(RError):
+            it.call("prepare_data_", from_py(Yb), from_py(Xb), from_py(float(tol)), from_py(float(maxit)), None,
+                    from_py(0.0), None, None)
+        with pytest.raises(ValueError):
+            prepare.prepare_data_(Yb, Xb, tol, maxit)
