@@ -177,10 +177,16 @@ def install_standin_helpers(it):
     g["checkpoint_"] = Builtin(no_checkpoint, "checkpoint_")
 
 
-def load(context_factory, helpers="standin"):
-    """-> (interpreter with atlasqtl_b200_core_ defined, the shim emulation)."""
+def load(context_factory=None, helpers="standin", shim="emulation"):
+    """-> (interpreter with atlasqtl_b200_core_ defined, the `.Call` object).  shim = "emulation": the Python emulation
+    of the C shim over context_factory; shim = "real": the shipped C shim itself, compiled against the stub R runtime
+    (tests/r_shim_real.py) and linked to libatlasqtl_b200.so (needs a GPU to get past aq_create)."""
     it = Interp()
-    shim = ShimEmulation(context_factory)
+    if shim == "real":
+        from r_shim_real import RealShim
+        shim = RealShim()
+    else:
+        shim = ShimEmulation(context_factory)
     g = it.globalenv.vars
     g[".Call"] = Builtin(shim, ".Call")
     for sym in SYMBOLS:
