@@ -56,7 +56,7 @@ def ncu_traffic(config, world):
         return None, f"stale: {rec.get('source')} was captured from other kernel sources ({rec.get('src_hash')})"
     return rec["bytes"], rec.get("source")
 
-FP64_PEAK_TFLOPS = 37.05  # measured DMMA m8n8k4 peak on this pool's B200 (profiles/r1_fp64_peaks_microbench.txt);
+FP64_PEAK_TFLOPS = 37.05  # measured DMMA m8n8k4 peak on this pool's B200 (profiles/r2_fp64_peaks_microbench.txt, with a clock record);
                           # MEASURED_PEAKS.json has no fp64 entry (bf16 / HBM only)
 
 
