@@ -33,7 +33,8 @@ def build():
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     cmd = ["gcc", "-O1", "-g", "-Wall", "-Wextra", "-Werror", "-Wno-cast-function-type", "-shared", "-fPIC", "-I", STUB,
-           "-I", os.path.join(ROOT, "include"), *srcs, "-L", LIBDIR, "-latlasqtl_b200", f"-Wl,-rpath,{LIBDIR}", "-o", OUT]
+           "-I", os.path.join(ROOT, "include"), *srcs, "-L", LIBDIR, "-latlasqtl_b200",
+           "-Wl,-rpath,$ORIGIN/../../../atlasqtl_b200", "-o", OUT]   # relative: the tree may be copied elsewhere
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("building the shim against the stub R runtime failed:\n" + res.stderr)
@@ -47,9 +48,18 @@ class StubPtr:
         self.sexp = sexp
 
 
+def load_library():
+    try:
+        return ctypes.CDLL(build())
+    except OSError:           # a stale build from another location / toolchain: rebuild once
+        if os.path.exists(OUT):
+            os.remove(OUT)
+        return ctypes.CDLL(build())
+
+
 class RealShim:
     def __init__(self):
-        self.lib = ctypes.CDLL(build())
+        self.lib = load_library()
         L = self.lib
         vp = ctypes.c_void_p
         L.rstub_wrap.restype = vp
