@@ -86,8 +86,8 @@ R_SEMANTICS = [
      [0.9750021048517795, -804.6084420137538, -3.7831843336820317]),
     ("c(.Machine$double.eps^0.5, digamma(1), lgamma(0.5), lfactorial(4))",
      [1.4901161193847656e-08, -0.5772156649015329, 0.5723649429247001, np.log(24.0)]),
-    ("log_one_plus <- function(x) { m <- x; m[x < 0] <- 0; log(exp(x - m) + exp(-m)) + m }; log_one_plus(c(-800, 0, 800))",
-     [0, np.log(2.0), 800]),
+    ("softplus <- function(v) { big <- v > 0; out <- log1p(exp(-abs(v))); out[big] <- out[big] + v[big]; out }; "
+     "softplus(c(-800, 0, 800))", [0, np.log(2.0), 800]),
     ("f <- function() { x <- 1; g <- function() x <<- x + 1; g(); x }; f()", [2]),
     ("tryCatch({ stop('boom'); 1 }, error = function(e) 2)", [2]),
     ("uniroot(function(x) x^2 - 2, interval = c(0, 2), tol = 1e-12)$root", [2 ** 0.5]),
