@@ -1546,6 +1546,57 @@ def sp_suppress(it, env, args):
     return v
 
 
+def sp_save(it, env, args):
+    """save(obj1, obj2, ..., file = path): the named objects, as an .npz archive standing in for R's .RData format
+    (lists are flattened to `name$field` entries)."""
+    path = None
+    objs = {}
+    for name, ex in args:
+        if name == "file":
+            path = it.eval(ex, env).a[0]
+        elif name is None and ex[0] == "id":
+            objs[ex[1]] = it.eval(ex, env)
+    if path is None:
+        raise RError("save(): 'file' must be specified")
+    flat = {}
+
+    def put(key, v):
+        if isinstance(v, RList):
+            for i, item in enumerate(v.items):
+                put(f"{key}${v.names[i] if v.names and v.names[i] else i + 1}", item)
+        elif isinstance(v, V):
+            flat[key] = v.a if v.a.dtype.kind != "O" else np.array([str(x) for x in v.a.reshape(-1)])
+        elif v is None:
+            flat[key] = np.zeros(0)
+    for k, v in objs.items():
+        put(k, v)
+    with open(path, "wb") as f:
+        np.savez(f, **flat)
+    return None
+
+
+def b_list_files(it, pos, named):
+    import re
+    path = _arg(pos, named, 0, "path", chr_(".")).a[0]
+    pattern = _arg(pos, named, 1, "pattern")
+    names = sorted(os.listdir(path)) if os.path.isdir(path) else []
+    if pattern is not None:
+        rx = re.compile(pattern.a[0])
+        names = [n for n in names if rx.search(n)]
+    return chr_(names) if names else V(np.empty(0, dtype=object))
+
+
+def b_file_remove(it, pos, named):
+    out = []
+    for f in _strs(pos[0]):
+        try:
+            os.remove(f)
+            out.append(True)
+        except OSError:
+            out.append(False)
+    return lgl(out)
+
+
 def sp_switch(it, env, args):
     sel = it.eval(args[0][1], env)
     alts = args[1:]
@@ -1665,18 +1716,20 @@ def install(it):
                      ("cbind", b_cbind(1)), ("rbind", b_cbind(0)), ("uniroot", b_uniroot), ("nchar", b_nchar),
                      ("numeric", b_numeric), ("diag", b_diag), ("outer", b_outer),
                      ("is.nan", b_is_elementwise(np.isnan)), ("is.finite", b_is_elementwise(np.isfinite)),
-                     ("is.infinite", b_is_elementwise(np.isinf))):
+                     ("is.infinite", b_is_elementwise(np.isinf)), ("list.files", b_list_files),
+                     ("file.remove", b_file_remove)):
         reg(name, fn)
     for kind in ("null", "list", "function", "vector", "matrix", "numeric", "double", "integer", "logical",
                  "character"):
         reg("is." + kind, b_is(kind))
     reg("dir.exists", lambda it_, p, n: lgl(os.path.isdir(p[0].a[0])))
-    reg("file.exists", lambda it_, p, n: lgl(os.path.exists(p[0].a[0])))
+    reg("file.exists", lambda it_, p, n: lgl([os.path.exists(f) for f in _strs(p[0])]))
     reg("Sys.time", lambda it_, p, n: dbl(0.0))
     for name, fn in (("with", sp_with), ("quote", sp_quote), ("substitute", sp_substitute), ("missing", sp_missing),
                      ("match.call", sp_match_call), ("rm", sp_rm), ("tryCatch", sp_tryCatch), ("return", sp_return),
                      ("library", sp_function_noop), ("require", sp_function_noop), ("set.seed", sp_function_noop),
-                     ("suppressWarnings", sp_suppress), ("switch", sp_switch), ("on.exit", sp_function_noop)):
+                     ("suppressWarnings", sp_suppress), ("switch", sp_switch), ("on.exit", sp_function_noop),
+                     ("save", sp_save)):
         reg(name, fn, special=True)
     g["pi"] = dbl(math.pi)
     g[".Machine"] = RList([dbl(np.finfo(np.float64).eps), intv(2 ** 31 - 1), dbl(np.finfo(np.float64).max),

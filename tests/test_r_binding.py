@@ -65,3 +65,43 @@ def test_r_binding_full_output_and_argument_checks(oracle_built):
     with pytest.raises(Exception, match="Batch scheme"):
         r_binding.load(lambda X, Y: OracleSweepContext(X, Y))[0].run(
             "atlasqtl_b200_core_(matrix(0, 2, 2), matrix(0, 2, 2), 2, NULL, 1, 0.1, 10, 0, list(), list(), batch = '0')")
+
+
+def test_r_binding_checkpoints_through_the_package_checkpoint_function(oracle_built, tmp_path):
+    """checkpoint_ / checkpoint_clean_up_ (R/utils.R:571-627) are the reference's own functions here: every 100th
+    non-annealed iteration the binding fetches gam_vb / beta_vb from the device (aq_get_state, two separately allocated
+    matrices) and hands them over; the files are removed at the end.  The case runs exactly 100 iterations."""
+    from oracle.rlite import reference as R
+    from oracle.rlite.values import Builtin, from_py, lgl
+    if not R.available():
+        pytest.skip("/root/reference is not present here")
+    g, hyper, init, anneal = load_case([f for f in CORE_FILES if "d_linear" in f][0])
+    assert int(g["it"]) == 100
+    it, shim = r_binding.load(lambda X, Y: OracleSweepContext(X, Y), helpers="reference")
+    seen = []
+    orig = it.globalenv.vars["checkpoint_clean_up_"]
+
+    def spy(it_, pos, named):
+        import glob
+        for f in sorted(glob.glob(str(tmp_path) + "/tmp_output_it_*.RData")):
+            seen.append((f, {k: v.copy() for k, v in np.load(f).items()}))
+        return it_.apply(orig, pos, named, it_.globalenv)
+    it.globalenv.vars["checkpoint_clean_up_"] = Builtin(spy, "checkpoint_clean_up_")
+    q = g["Y"].shape[1]
+    from oracle.rlite.values import RList
+    out = it.call("atlasqtl_b200_core_", from_py(np.array(g["Y"], order="F")), from_py(np.array(g["X"], order="F")),
+                  from_py(float(q)), from_py(np.asarray(anneal, dtype=np.float64)), from_py(1.0), from_py(float(g["tol"])),
+                  from_py(1000.0), from_py(0.0),
+                  RList([from_py(np.asarray(v, dtype=np.float64)) for v in hyper.values()], list(hyper.keys())),
+                  RList([from_py(np.array(v, dtype=np.float64, order="F")) for v in init.values()], list(init.keys())),
+                  checkpoint_path=from_py(str(tmp_path) + "/"), debug=lgl(True))
+    assert len(seen) == 1 and seen[0][0].endswith("tmp_output_it_100.RData")
+    ck = seen[0][1]
+    assert int(ck["tmp_vb$it"][0]) == 100 and bool(ck["tmp_vb$converged"][0])
+    np.testing.assert_allclose(ck["tmp_vb$gam_vb"], g["gam_vb"], atol=1e-9)       # the state of iteration 100 = the final one
+    np.testing.assert_allclose(ck["tmp_vb$beta_vb"], g["beta_vb"], atol=1e-9)
+    assert not np.shares_memory(ck["tmp_vb$gam_vb"], ck["tmp_vb$beta_vb"]) and np.abs(ck["tmp_vb$gam_vb"] - ck["tmp_vb$beta_vb"]).max() > 0
+    import glob
+    assert glob.glob(str(tmp_path) + "/tmp_output_it_*") == []                      # checkpoint_clean_up_ removed it
+    assert shim.calls["_atlasqtl_aq_get_state"] == 2
+    assert np.abs(np.asarray(out.get("gam_vb").a) - g["gam_vb"]).max() <= 1e-9
