@@ -11,6 +11,17 @@ from rlite_cases import CORE_FILES, CORE_IDS, load_case
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(scope="module", autouse=True)
+def shim_library():
+    """The shim + stub runtime are compiled with gcc at test time; a box without a C compiler skips (the build itself is
+    covered by the CPU suite, tests/test_r_shim_real.py)."""
+    import r_shim_real
+    try:
+        r_shim_real.load_library()
+    except (RuntimeError, OSError) as e:
+        pytest.skip(f"cannot build / load the shim against the stub R runtime here: {e}")
+
+
 @pytest.mark.parametrize("path", CORE_FILES, ids=CORE_IDS)
 def test_r_loop_through_the_real_shim_on_the_cuda_library(path):
     import r_binding
