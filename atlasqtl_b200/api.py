@@ -9,6 +9,31 @@ import numpy as np
 from . import core, hyper_init, prepare
 
 
+def add_collinear_back_(beta_vb, gam_vb, theta_vb, names_x, initial_colnames_X, rmvd_coll_x):
+    """R/utils.R:680-735: the posterior summaries with one row per NON-CONSTANT predictor again -- a predictor removed as
+    a duplicate gets the rows of the predictor it duplicates.  rmvd_coll_x: {kept name: [removed names]}
+    (names(rmvd_coll_x) -> rmvd_coll_x in R).  Returns beta_vb, gam_vb, theta_vb and names_x over initial_colnames_X."""
+    pos = {nm: i for i, nm in enumerate(initial_colnames_X)}
+    kept_rows = np.array([pos[nm] for nm in names_x])
+    p_all, q = len(initial_colnames_X), gam_vb.shape[1]
+    out = {}
+    for key, arr in (("beta_vb", beta_vb), ("gam_vb", gam_vb)):
+        full = np.full((p_all, q), np.nan, order="F")
+        full[kept_rows] = arr
+        for kept, removed in rmvd_coll_x.items():
+            for nm in removed:
+                full[pos[nm]] = full[pos[kept]]
+        out[key] = full
+    th = np.full(p_all, np.nan)
+    th[kept_rows] = theta_vb
+    for kept, removed in rmvd_coll_x.items():
+        for nm in removed:
+            th[pos[nm]] = th[pos[kept]]
+    out["theta_vb"] = th
+    out["names_x"] = list(initial_colnames_X)
+    return out
+
+
 def atlasqtl(Y, X, p0, anneal=(1, 2, 10), tol=0.1, maxit=1000, user_seed=None, verbose=1, list_hyper=None,
              list_init=None, save_hyper=False, save_init=False, full_output=False, thinned_elbo_eval=True,
              checkpoint_path=None, trace_path=None, add_collinear_back=False, *, device=0, comm=None, order_fn=None,
@@ -45,8 +70,8 @@ def atlasqtl(Y, X, p0, anneal=(1, 2, 10), tol=0.1, maxit=1000, user_seed=None, v
         list_init = hyper_init.auto_set_init_(Yp, p, p0, shr_fac_inv, user_seed, root=hyper_root)
     elif list_init["p_init"] != p or list_init["q_init"] != q:
         raise ValueError("The dimensions of list_init do not match those of the (pre-processed) data.")
-    if add_collinear_back:
-        raise NotImplementedError("add_collinear_back is host-side post-processing outside this path")
+    if add_collinear_back and comm is not None and comm.world_size > 1:
+        raise NotImplementedError("add_collinear_back under a communicator: apply add_collinear_back_ to the gathered result")
 
     df = 1  # R/atlasqtl.R:272 (hs <- TRUE, debug <- TRUE)
     slab = None
@@ -67,6 +92,9 @@ def atlasqtl(Y, X, p0, anneal=(1, 2, 10), tol=0.1, maxit=1000, user_seed=None, v
     res["rmvd_cst_x"] = dat["rmvd_cst_x"]
     res["rmvd_coll_x"] = dat["rmvd_coll_x"]
     res["names_x"], res["names_y"] = dat["names_x"], dat["names_y"]
+    if add_collinear_back and len(dat["rmvd_coll_x"]) > 0:  # R/atlasqtl.R:297-310
+        res.update(add_collinear_back_(res["beta_vb"], res["gam_vb"], res["theta_vb"], dat["names_x"],
+                                       dat["initial_colnames_X"], dat["rmvd_coll_x"]))
     if save_hyper:
         res["list_hyper"] = list_hyper
     if save_init:

@@ -306,8 +306,11 @@ def index_assign(it, obj, pos, named, double, val):
         return lst
     if not isinstance(val, V):
         raise RError("replacement value must be an atomic vector")
-    if obj is None:
-        obj = V(np.zeros(0, dtype=val.a.dtype))
+    if obj is None:   # NULL[i] <- value creates the vector (NA where nothing is assigned)
+        n0 = pos[0].a.size if len(pos) == 1 and isinstance(pos[0], V) and pos[0].a.dtype.kind == "b" else 0
+        init = np.empty(n0, dtype=val.a.dtype if val.a.dtype.kind in "fO" else np.float64)
+        init[:] = _na_of(init.dtype)
+        obj = V(init)
     a = _promote(obj.a, val.a)
     if len(pos) == 1:
         i = pos[0]

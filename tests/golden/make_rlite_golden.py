@@ -158,6 +158,14 @@ def make_top(it):
     it.globalenv.vars["elbo_global_local_"] = orig
     o = to_py(out)
     assert bool(o["converged"][0])
+    # the same call with add_collinear_back = TRUE (add_collinear_back_, R/utils.R:680-735): one row per non-constant
+    # predictor again, a removed duplicate carrying the rows of the predictor it duplicates
+    cb = it.call("atlasqtl", Y=R._copy_in(Y), X=R._copy_in(X), p0=None, anneal=from_py(np.array(anneal, float)),
+                 tol=from_py(0.1), maxit=from_py(1000.0), verbose=from_py(0.0),
+                 list_hyper=R.with_class(R._copy_in(hyper), "out_hyper"),
+                 list_init=R.with_class(R._copy_in(init), "out_init"), add_collinear_back=from_py(True))
+    cb_names = np.array(cb.get("gam_vb").dimnames[0], dtype="U")
+    assert list(cb.get("theta_vb").names) == list(cb_names)
     print(f"  atlasqtl(): p_raw={X.shape[1]} -> p={p}, removed constant {list(prep.get('rmvd_cst_x').a)}, collinear "
           f"{list(rm_coll.a)} (kept {rm_coll.names}); it={int(o['it'][0])}", flush=True)
     save("rlite_atlasqtl_top.npz", X_raw=X, Y_raw=Y, anneal=np.array(anneal, float), tol=0.1,
@@ -168,7 +176,8 @@ def make_top(it):
          names_x=np.array(out.get("gam_vb").dimnames[0], dtype="U"), names_y=np.array(out.get("gam_vb").dimnames[1], dtype="U"),
          **{"hyper_" + k: np.asarray(v) for k, v in hyper.items()}, **{"init_" + k: np.asarray(v) for k, v in init.items()},
          lb=np.array(lbs), it=int(o["it"][0]), converged=True, lb_opt=float(o["lb_opt"][0]), diff_lb=float(o["diff_lb"][0]),
-         gam_vb=o["gam_vb"], beta_vb=o["beta_vb"], theta_vb=o["theta_vb"], zeta_vb=o["zeta_vb"])
+         gam_vb=o["gam_vb"], beta_vb=o["beta_vb"], theta_vb=o["theta_vb"], zeta_vb=o["zeta_vb"],
+         cb_names_x=cb_names, cb_gam_vb=cb.get("gam_vb").a, cb_beta_vb=cb.get("beta_vb").a, cb_theta_vb=cb.get("theta_vb").a)
 
 
 def make_functions(it):

@@ -284,6 +284,17 @@ def test_preprocessing_and_top_level_call_reproduce_the_reference_r_code(oracle_
     assert np.max(np.abs(lb - g["lb"]) / np.abs(g["lb"])) <= 1e-10
     for k in ("gam_vb", "beta_vb", "theta_vb", "zeta_vb"):
         assert np.max(np.abs(out[k] - g[k])) <= 1e-9, k
+    # add_collinear_back = TRUE (add_collinear_back_, R/utils.R:680-735): rows for the removed duplicates again
+    back = api.atlasqtl(Y, X, None, anneal=tuple(g["anneal"]), tol=float(g["tol"]), maxit=1000, verbose=0,
+                        list_hyper=hyper, list_init=init, add_collinear_back=True,
+                        context_factory=lambda X_, Y_: OracleSweepContext(X_, Y_))
+    assert back["names_x"] == list(g["cb_names_x"]) and back["gam_vb"].shape == g["cb_gam_vb"].shape
+    for k in ("gam_vb", "beta_vb", "theta_vb"):
+        assert not np.isnan(back[k]).any()
+        assert np.max(np.abs(back[k] - g["cb_" + k])) <= 1e-9, k
+    rows = {nm: i for i, nm in enumerate(back["names_x"])}
+    for kept, removed in zip(g["prep_rmvd_coll_kept"], g["prep_rmvd_coll_x"]):
+        assert np.array_equal(back["gam_vb"][rows[removed]], back["gam_vb"][rows[kept]])
 
 
 # --------------------------------------------------------------------------------------------- live re-derivation
